@@ -1,0 +1,312 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+* :func:`bn_mcmc`  -- ``R/bn_mcmc.R:8-25``  (same arguments and defaults)
+* :func:`main_fun` -- ``src/bayesnet_mcmc.cpp:27-38`` (same arguments and defaults;
+  result columns ``iter, ChangedNode, movetype, globalLL, additions, deletions, FN, FP``
+  as in ``network::result``, ``src/network.h:353-364``)
+* :class:`Context` -- the C ABI of ``include/bn_b200.h`` one level up: sufficient
+  statistics once per dataset, then scoring / chains on the device.
+
+Every compute call goes through ``libbn_b200.so``; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BN_RNG_REPLAY, BN_RNG_RMT, BN_RNG_WH, BnError, as_i32, check, ptr
+from .network import Network
+
+TRACE_COLUMNS = ("iter", "ChangedNode", "movetype", "globalLL", "additions", "deletions", "FN", "FP")
+_RNG_KINDS = {"wh": BN_RNG_WH, "rmt": BN_RNG_RMT, "replay": BN_RNG_REPLAY,
+              BN_RNG_WH: BN_RNG_WH, BN_RNG_RMT: BN_RNG_RMT, BN_RNG_REPLAY: BN_RNG_REPLAY}
+
+
+@dataclass
+class ChainResult:
+    """One chain: the eight trace columns plus counters and the final graph."""
+    trace: dict
+    uniforms: int
+    valid_iters: int
+    proposed: tuple
+    reject: tuple
+    n_nonpd: int
+    total_edges: int
+    windows: int
+    alg_bytes: int
+    final_parents: np.ndarray   # [P, max_par], -1 padded, per-child list order
+    final_npar: np.ndarray
+    accepted_moves: Optional[np.ndarray] = None  # rows (iter, movetype, child, parent)
+    edge_freq: Optional[np.ndarray] = None       # [child, parent] counts (posterior tabulation)
+
+    def edges(self):
+        """(parent, child) pairs, 0-based, per-child list order."""
+        return [(int(self.final_parents[c, e]), c)
+                for c in range(len(self.final_npar)) for e in range(int(self.final_npar[c]))]
+
+
+class Context:
+    """Device-resident sufficient statistics + prior graph (``bn_ctx``)."""
+
+    def __init__(self, handle, n_samples, n_nodes, max_par):
+        self._h = handle
+        self.n_samples, self.n_nodes, self.max_par = n_samples, n_nodes, max_par
+
+    # -- constructors --------------------------------------------------------
+    @staticmethod
+    def _graph_args(graph_source, graph_target, graph_node_type, n_nodes):
+        src, tgt = as_i32(graph_source), as_i32(graph_target)
+        if src.shape != tgt.shape:
+            raise ValueError("graph_source and graph_target must have the same length")
+        nt = as_i32(graph_node_type)
+        if nt.shape != (n_nodes,):
+            raise ValueError("graph_node_type must have one entry per column of X")
+        return src, tgt, nt
+
+    @classmethod
+    def from_data(cls, X, graph_source, graph_target, graph_node_type, max_par=50, phi=1.0,
+                  omega=6.9, device=0):
+        """``X``: (n_samples, n_nodes) float64; stored column-major like R's matrix."""
+        Xf = np.asfortranarray(np.asarray(X, dtype=np.float64))
+        n, p = Xf.shape
+        src, tgt, nt = cls._graph_args(graph_source, graph_target, graph_node_type, p)
+        h = C.c_void_p()
+        check(_lib.lib().bn_create(ptr(Xf), n, p, ptr(src), ptr(tgt), len(src), ptr(nt), int(max_par),
+                                   float(phi), float(omega), int(device), C.byref(h)))
+        return cls(h, n, p, int(max_par))
+
+    @classmethod
+    def from_device(cls, data_ptr, ld, n_samples, n_nodes, graph_source, graph_target,
+                    graph_node_type, max_par=50, phi=1.0, omega=6.9, device=0):
+        """X already in HBM (column-major, leading dimension ``ld``), e.g. ``tensor.data_ptr()``."""
+        src, tgt, nt = cls._graph_args(graph_source, graph_target, graph_node_type, n_nodes)
+        h = C.c_void_p()
+        check(_lib.lib().bn_create_from_device(C.c_void_p(int(data_ptr)), int(ld), int(n_samples),
+                                               int(n_nodes), ptr(src), ptr(tgt), len(src), ptr(nt),
+                                               int(max_par), float(phi), float(omega), int(device),
+                                               C.byref(h)))
+        return cls(h, int(n_samples), int(n_nodes), int(max_par))
+
+    @classmethod
+    def from_stats(cls, n_samples, mean, centered_gram, graph_source, graph_target,
+                   graph_node_type, max_par=50, phi=1.0, omega=6.9, device=0):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        cg = np.ascontiguousarray(centered_gram, dtype=np.float64)
+        p = mean.shape[0]
+        if cg.shape != (p, p):
+            raise ValueError("centered_gram must be (n_nodes, n_nodes)")
+        src, tgt, nt = cls._graph_args(graph_source, graph_target, graph_node_type, p)
+        h = C.c_void_p()
+        check(_lib.lib().bn_create_from_stats(int(n_samples), p, ptr(mean), ptr(cg), ptr(src), ptr(tgt),
+                                              len(src), ptr(nt), int(max_par), float(phi),
+                                              float(omega), int(device), C.byref(h)))
+        return cls(h, int(n_samples), p, int(max_par))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _lib.lib().bn_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection -------------------------------------------------------
+    def set_stream(self, cuda_stream: Optional[int]):
+        check(_lib.lib().bn_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    @property
+    def gram_ms(self) -> float:
+        ms = C.c_float(0)
+        check(_lib.lib().bn_get_gram_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().bn_get_launch_count(self._h))
+
+    def stats(self):
+        """(sumX, sumXX, mean, centered): ``src/network.h:124-136`` + the centred form used here."""
+        p = self.n_nodes
+        sum_x, mean = np.empty(p), np.empty(p)
+        sum_xx = np.empty((p, p), order="F")
+        centered = np.empty((p, p))
+        check(_lib.lib().bn_get_stats(self._h, ptr(sum_x), ptr(sum_xx), ptr(mean), ptr(centered)))
+        return sum_x, np.ascontiguousarray(sum_xx), mean, centered
+
+    # -- scoring -------------------------------------------------------------
+    def score_nodes(self, child, parents, n_par):
+        """``network::score`` for explicit (child, ordered parent list) items."""
+        child, n_par = as_i32(child), as_i32(n_par)
+        parents = as_i32(parents)
+        n = child.shape[0]
+        if parents.shape != (n, self.max_par):
+            raise ValueError(f"parents must be ({n}, {self.max_par})")
+        out = np.empty(n)
+        check(_lib.lib().bn_score_nodes(self._h, n, ptr(child), ptr(parents), ptr(n_par), ptr(out)))
+        return out
+
+    def score_all_proposals(self, parents, n_par, want_score=True, want_log_hr=True):
+        """Every add/delete proposal of each DAG; returns (base, score, log_hr)."""
+        parents, n_par = as_i32(parents), as_i32(n_par)
+        if parents.ndim == 2:
+            parents, n_par = parents[None], n_par[None]
+        g, p = n_par.shape
+        if parents.shape != (g, p, self.max_par) or p != self.n_nodes:
+            raise ValueError("parents must be (n_graphs, n_nodes, max_par)")
+        base = np.empty((g, p))
+        score = np.empty((g, p, p)) if want_score else None
+        hr = np.empty((g, p, p)) if want_log_hr else None
+        check(_lib.lib().bn_score_all_proposals(self._h, g, ptr(parents), ptr(n_par), ptr(base),
+                                                ptr(score), ptr(hr)))
+        return base, score, hr
+
+    def score_all_proposals_device(self, n_graphs, d_parents, d_npar, d_base, d_score, d_log_hr):
+        """Device-pointer variant; returns the device time of the launch in ms."""
+        ms = C.c_float(0)
+        check(_lib.lib().bn_score_all_proposals_device(
+            self._h, int(n_graphs), C.c_void_p(d_parents), C.c_void_p(d_npar), C.c_void_p(d_base or 0),
+            C.c_void_p(d_score or 0), C.c_void_p(d_log_hr or 0), C.byref(ms)))
+        return float(ms.value)
+
+    # -- chains --------------------------------------------------------------
+    def run(self, n_chains=1, n_iter=1000, output=100, initial_network=2, drop=0, rng="wh",
+            seeds=None, replay=None, log_moves=False, moves_capacity=None, tabulate=False):
+        """Run ``n_chains`` independent chains; returns (list[ChainResult], kernel_ms)."""
+        L = _lib.lib()
+        kind = _RNG_KINDS[rng]
+        p, mp = self.n_nodes, self.max_par
+        cap = max(1, (n_iter + output - 1) // output)
+        ints = {k: np.zeros((n_chains, cap), dtype=np.int32) for k in
+                ("iter", "ChangedNode", "movetype", "additions", "deletions", "FN", "FP")}
+        gll = np.zeros((n_chains, cap))
+        n_rows = np.zeros(n_chains, dtype=np.int32)
+        tr = _lib.Trace(cap, n_rows.ctypes.data_as(_lib._ip), ints["iter"].ctypes.data_as(_lib._ip),
+                        ints["ChangedNode"].ctypes.data_as(_lib._ip),
+                        ints["movetype"].ctypes.data_as(_lib._ip), gll.ctypes.data_as(_lib._dp),
+                        ints["additions"].ctypes.data_as(_lib._ip),
+                        ints["deletions"].ctypes.data_as(_lib._ip), ints["FN"].ctypes.data_as(_lib._ip),
+                        ints["FP"].ctypes.data_as(_lib._ip))
+        args = _lib.RunArgs()
+        args.n_chains, args.rng_kind = int(n_chains), int(kind)
+        sd = None
+        if seeds is not None:
+            sd = np.zeros((n_chains, 3), dtype=np.int32)
+            s_in = np.asarray(seeds, dtype=np.int64)
+            if s_in.ndim == 0:
+                s_in = s_in.reshape(1, 1)
+            if s_in.ndim == 1:
+                s_in = s_in.reshape(n_chains, -1) if n_chains > 1 else s_in.reshape(1, -1)
+            sd[:, :s_in.shape[1]] = s_in
+            args.seeds = sd.ctypes.data_as(_lib._ip)
+        rp = None
+        if kind == BN_RNG_REPLAY:
+            rp = np.ascontiguousarray(replay, dtype=np.float64)
+            if rp.ndim == 1:
+                rp = rp[None]
+            if rp.shape[0] != n_chains:
+                raise ValueError("replay must be (n_chains, replay_len)")
+            args.replay = rp.ctypes.data_as(_lib._dp)
+            args.replay_len = rp.shape[1]
+        args.initial_network, args.drop = int(initial_network), int(drop)
+        args.n_iter, args.output_every, args.device_outputs = int(n_iter), int(output), 0
+        moves = n_moves = None
+        if log_moves:
+            mc = int(moves_capacity if moves_capacity is not None else n_iter)
+            moves = np.zeros((n_chains, max(mc, 1), 4), dtype=np.int32)
+            n_moves = np.zeros(n_chains, dtype=np.int32)
+            args.moves_capacity = moves.shape[1]
+            args.moves = moves.ctypes.data_as(_lib._ip)
+            args.n_moves = n_moves.ctypes.data_as(_lib._ip)
+        freq = None
+        if tabulate:
+            freq = np.zeros((n_chains, p, p), dtype=np.int32)
+            args.edge_freq = freq.ctypes.data_as(_lib._ip)
+        fpar = np.full((n_chains, p, mp), -1, dtype=np.int32)
+        fnpar = np.zeros((n_chains, p), dtype=np.int32)
+        stats = (_lib.ChainStats * n_chains)()
+        ms = C.c_float(0)
+        status = L.bn_run(self._h, C.byref(args), C.byref(tr), ptr(fpar), ptr(fnpar),
+                          C.cast(stats, C.c_void_p), C.byref(ms))
+        check(status)
+        out = []
+        for ch in range(n_chains):
+            r = int(n_rows[ch])
+            trace = {k: ints[k][ch, :r].copy() for k in ("iter", "ChangedNode", "movetype")}
+            trace["globalLL"] = gll[ch, :r].copy()
+            for k in ("additions", "deletions", "FN", "FP"):
+                trace[k] = ints[k][ch, :r].copy()
+            s = stats[ch]
+            fp_ch = fpar[ch].copy()
+            for c_ in range(p):
+                fp_ch[c_, fnpar[ch, c_]:] = -1
+            out.append(ChainResult(
+                trace=trace, uniforms=int(s.uniforms), valid_iters=int(s.valid_iters),
+                proposed=tuple(s.proposed), reject=tuple(s.reject), n_nonpd=int(s.n_nonpd),
+                total_edges=int(s.total_edges), windows=int(s.windows), alg_bytes=int(s.alg_bytes),
+                final_parents=fp_ch,
+                final_npar=fnpar[ch].copy(),
+                accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])].copy(),
+                edge_freq=None if freq is None else freq[ch].copy()))
+        return out, float(ms.value)
+
+
+# ---------------------------------------------------------------------------
+# the reference's two entry points
+# ---------------------------------------------------------------------------
+def main_fun(X, graph_source: Sequence[int], graph_target: Sequence[int],
+             graph_node_labels: Sequence[int], graph_node_type: Sequence[int], MaxPar: int = 50,
+             phi: float = 1, omega: float = 6.9, InitialNetwork: int = 2, drop: int = 0,
+             N: int = 1000, output: int = 10, *, rng="wh", seed=None) -> dict:
+    """``main_fun`` of ``src/bayesnet_mcmc.cpp:27-38`` through the C ABI (``bn_main_fun``).
+
+    ``rng``/``seed`` choose the uniform stream that stands in for ``R::runif``:
+    ``"wh"`` (Wichmann-Hill, ``seed`` = (ix, iy, iz) or None for the reference's
+    10437/13568/30524) or ``"rmt"`` (R's Mersenne-Twister, ``seed`` as in ``set.seed``).
+    Returns the eight result columns as arrays, in the reference's order.
+    """
+    Xf = np.asfortranarray(np.asarray(X, dtype=np.float64))
+    n, p = Xf.shape
+    src, tgt = as_i32(graph_source), as_i32(graph_target)
+    labels, nt = as_i32(graph_node_labels), as_i32(graph_node_type)
+    if src.shape != tgt.shape:
+        raise ValueError("graph_source and graph_target must have the same length")
+    kind = _RNG_KINDS[rng]
+    sd = None
+    if seed is not None:
+        sd = np.zeros(3, dtype=np.int32)
+        s_in = np.atleast_1d(np.asarray(seed, dtype=np.int64))
+        sd[:len(s_in)] = s_in
+    elif kind == BN_RNG_RMT:
+        raise ValueError("rng='rmt' needs seed= (the value given to set.seed)")
+    cap = max(1, (int(N) + int(output) - 1) // int(output)) if output > 0 else 1
+    cols = {k: np.zeros(cap, dtype=np.float64 if k == "globalLL" else np.int32) for k in TRACE_COLUMNS}
+    rows = _lib.lib().bn_main_fun(ptr(Xf), n, p, ptr(src), ptr(tgt), len(src), ptr(labels), ptr(nt),
+                                  int(MaxPar), float(phi), float(omega), int(InitialNetwork),
+                                  int(drop), int(N), int(output), int(kind), ptr(sd), cap,
+                                  *[ptr(cols[k]) for k in TRACE_COLUMNS])
+    if rows < 0:
+        raise BnError(-rows, _lib.lib().bn_last_error().decode("utf-8", "replace"))
+    return {k: cols[k][:rows].copy() for k in TRACE_COLUMNS}
+
+
+def bn_mcmc(X, graph: Network, MaxPar: int = 50, phi: float = 1, omega: float = 6.9,
+            InitialNetwork: int = 2, drop: int = 0, N: int = 1000, output: int = 100, *,
+            rng="wh", seed=None) -> dict:
+    """``bn_mcmc`` of ``R/bn_mcmc.R:8-25``: unpack the network object and forward to main_fun."""
+    return main_fun(X=X, graph_target=graph.target, graph_source=graph.source,
+                    graph_node_labels=np.arange(graph.n_nodes, dtype=np.int32),
+                    graph_node_type=graph.node_type_codes(), MaxPar=MaxPar, phi=phi, omega=omega,
+                    InitialNetwork=InitialNetwork, drop=drop, N=N, output=output, rng=rng, seed=seed)

@@ -1,0 +1,623 @@
+// The extern "C" layer of libbn_b200.so (include/bn_b200.h): context management,
+// host<->device marshalling, kernel launches.  No compute happens on the host.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bn_b200.h"
+#include "gram.h"
+#include "kernels.h"
+
+using namespace bn;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_TRY(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(e_ == cudaErrorMemoryAllocation ? BN_ERR_OOM : BN_ERR_CUDA, "%s: %s (%s:%d)", \
+                  #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                       \
+  } while (0)
+
+extern "C" const char* bn_last_error(void) { return g_err; }
+extern "C" int bn_abi_version(void) { return BN_B200_ABI_VERSION; }
+extern "C" int bn_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct bn_ctx {
+  int device = 0;
+  int n_sms = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int n_samples = 0, P = 0, max_par = 0, n_sim_edges = 0;
+  double phi = 1, omega = 6.9;
+  double* d_C = nullptr;       // centred Gram [P][P]
+  double* d_diag = nullptr;    // [P]
+  double* d_mean = nullptr;    // [P]
+  double* d_colsum = nullptr;  // [P]
+  uint8_t* d_node_type = nullptr;
+  uint8_t* d_sim_edge = nullptr;  // [parent + child*P]
+  int* d_prior_par = nullptr;     // [P][max_par]
+  int* d_prior_npar = nullptr;    // [P]
+  float gram_ms = 0.f;
+  int64_t launches = 0;
+  std::vector<void*> owned;  // device allocations freed by bn_destroy
+};
+
+template <typename T>
+static cudaError_t dalloc(bn_ctx* c, T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1);
+  if (e == cudaSuccess && c) c->owned.push_back((void*)*p);
+  return e;
+}
+
+extern "C" void bn_destroy(bn_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (void* p : c->owned) cudaFree(p);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+static int check_graph_args(int n_samples, int P, const int* src, const int* tgt, int n_edges,
+                            const int* node_type, int max_par) {
+  if (n_samples < 3) return fail(BN_ERR_BAD_ARG, "n_samples must be >= 3 (got %d)", n_samples);
+  if (P < 2 || P > 65535) return fail(BN_ERR_BAD_ARG, "n_nodes must be in [2, 65535] (got %d)", P);
+  if (max_par < 1) return fail(BN_ERR_BAD_ARG, "max_par must be >= 1 (got %d)", max_par);
+  if (max_par > 64) return fail(BN_ERR_UNSUPPORTED, "max_par > 64 is not supported (got %d)", max_par);
+  if (n_edges < 0 || (n_edges > 0 && (!src || !tgt))) return fail(BN_ERR_BAD_ARG, "bad edge list");
+  if (!node_type) return fail(BN_ERR_BAD_ARG, "node_type is NULL");
+  for (int p = 0; p < P; p++)
+    if (node_type[p] < 0 || node_type[p] > 2)
+      return fail(BN_ERR_BAD_ARG, "node_type[%d] = %d is not 0/1/2", p, node_type[p]);
+  for (int e = 0; e < n_edges; e++)
+    if (src[e] < 1 || src[e] > P || tgt[e] < 1 || tgt[e] > P)
+      return fail(BN_ERR_BAD_ARG, "edge %d (%d -> %d) out of range 1..%d", e, src[e], tgt[e], P);
+  return BN_OK;
+}
+
+// device selection + graph/prior upload shared by the three constructors
+static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n_edges, const int* node_type,
+                     int max_par, double phi, double omega, int device, bn_ctx** out) {
+  if (!out) return fail(BN_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  int rc = check_graph_args(n_samples, P, src, tgt, n_edges, node_type, max_par);
+  if (rc) return rc;
+  int ndev = bn_device_count();
+  if (ndev <= 0) return fail(BN_ERR_NO_DEVICE, "no CUDA device available (libbn_b200 has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(BN_ERR_NO_DEVICE, "device %d out of range (0..%d)", device, ndev - 1);
+  CU_TRY(cudaSetDevice(device));
+  bn_ctx* c = new bn_ctx();
+  c->device = device;
+  c->n_samples = n_samples; c->P = P; c->max_par = max_par; c->phi = phi; c->omega = omega;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sms = prop.multiProcessorCount;
+  *out = c;  // from here on the caller destroys on failure
+  CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+
+  // parent lists edges[tgt-1].push_back(src-1), src/network.h:117-120
+  std::vector<int> par((size_t)P * max_par, -1), npar(P, 0);
+  std::vector<uint8_t> sim((size_t)P * P, 0), types(P);
+  for (int e = 0; e < n_edges; e++) {
+    const int child = tgt[e] - 1, parent = src[e] - 1;
+    if (npar[child] >= max_par) {
+      return fail(BN_ERR_BAD_ARG, "node %d has more than max_par=%d parents in the supplied graph", child, max_par);
+    }
+    par[(size_t)child * max_par + npar[child]++] = parent;
+    // simEdge(parent, child) = 1; NsimEdges counts list entries, src/network.h:140-145
+    sim[(size_t)parent + (size_t)child * P] = 1;
+    c->n_sim_edges++;
+  }
+  for (int p = 0; p < P; p++) types[p] = (uint8_t)node_type[p];
+  CU_TRY(dalloc(c, &c->d_prior_par, par.size()));
+  CU_TRY(dalloc(c, &c->d_prior_npar, npar.size()));
+  CU_TRY(dalloc(c, &c->d_sim_edge, sim.size()));
+  CU_TRY(dalloc(c, &c->d_node_type, types.size()));
+  CU_TRY(dalloc(c, &c->d_C, (size_t)P * P));
+  CU_TRY(dalloc(c, &c->d_diag, (size_t)P));
+  CU_TRY(dalloc(c, &c->d_mean, (size_t)P));
+  CU_TRY(dalloc(c, &c->d_colsum, (size_t)P));
+  CU_TRY(cudaMemcpy(c->d_prior_par, par.data(), par.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(c->d_prior_npar, npar.data(), npar.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(c->d_sim_edge, sim.data(), sim.size(), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(c->d_node_type, types.data(), types.size(), cudaMemcpyHostToDevice));
+  return BN_OK;
+}
+
+// X on the device (dX, ldx) -> d_C.  If inplace, dX is the context's padded buffer.
+static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc, const GramPlan& pl) {
+  double *d_partial = nullptr, *d_scratch = nullptr;
+  int* d_flag = nullptr;
+  CU_TRY(cudaMalloc((void**)&d_partial, (size_t)pl.workspace_bytes));
+  cudaError_t e1 = cudaMalloc((void**)&d_scratch, (size_t)c->P * GRAM_MEAN_MAX_CHUNKS * sizeof(double));
+  cudaError_t e2 = cudaMalloc((void**)&d_flag, sizeof(int));
+  int rc = BN_OK;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(BN_ERR_OOM, "gram scratch allocation failed");
+  if (!rc) {
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, c->stream);
+    const char* msg = gram_build(dX, ldx, c->n_samples, c->P, dXc, pl.ld_centered, d_partial, pl, c->d_colsum,
+                                 c->d_mean, c->d_C, c->P, d_scratch, d_flag, c->stream, &c->launches);
+    if (msg) rc = fail(BN_ERR_CUDA, "gram_build: %s", msg);
+  }
+  if (!rc) {
+    launch_diag(c->d_C, c->P, c->P, c->d_diag, c->stream);
+    c->launches++;
+    cudaEventRecord(ev1, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "gram kernels: %s", cudaGetErrorString(e));
+  }
+  if (!rc) {
+    cudaEventElapsedTime(&c->gram_ms, ev0, ev1);
+    int flag = 0;
+    cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    if (flag) rc = fail(BN_ERR_CUDA, "gram_dmma_kernel: TMA pipeline timed out (flag %d)", flag);
+  }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  cudaFree(d_partial); cudaFree(d_scratch); cudaFree(d_flag);
+  return rc;
+}
+
+extern "C" int bn_create(const double* X, int n_samples, int P, const int* src, const int* tgt, int n_edges,
+                         const int* node_type, int max_par, double phi, double omega, int device,
+                         bn_ctx** out) {
+  if (!X) return fail(BN_ERR_BAD_ARG, "X is NULL");
+  int rc = ctx_begin(n_samples, P, src, tgt, n_edges, node_type, max_par, phi, omega, device, out);
+  if (rc) { if (out && *out) { bn_destroy(*out); *out = nullptr; } return rc; }
+  bn_ctx* c = *out;
+  const GramPlan pl = gram_plan(n_samples, P, c->n_sms);
+  double* dXc = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
+  if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the device copy of X"); }
+  // column p of the R matrix is contiguous: one pitched copy into the padded buffer
+  e = cudaMemcpy2DAsync(dXc, (size_t)pl.ld_centered * 8, X, (size_t)n_samples * 8, (size_t)n_samples * 8,
+                        (size_t)P, cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "H2D copy of X: %s", cudaGetErrorString(e));
+  if (!rc) rc = ctx_build_gram(c, dXc, pl.ld_centered, dXc, pl);  // centred in place
+  cudaFree(dXc);
+  if (rc) { bn_destroy(c); *out = nullptr; }
+  return rc;
+}
+
+extern "C" int bn_create_from_device(const double* dX, int64_t ld, int n_samples, int P, const int* src,
+                                     const int* tgt, int n_edges, const int* node_type, int max_par,
+                                     double phi, double omega, int device, bn_ctx** out) {
+  if (!dX) return fail(BN_ERR_BAD_ARG, "dX is NULL");
+  if (ld < n_samples) return fail(BN_ERR_BAD_ARG, "ld < n_samples");
+  int rc = ctx_begin(n_samples, P, src, tgt, n_edges, node_type, max_par, phi, omega, device, out);
+  if (rc) { if (out && *out) { bn_destroy(*out); *out = nullptr; } return rc; }
+  bn_ctx* c = *out;
+  const GramPlan pl = gram_plan(n_samples, P, c->n_sms);
+  double* dXc = nullptr;
+  cudaError_t e = cudaMalloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
+  if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the centred copy of X"); }
+  rc = ctx_build_gram(c, dX, ld, dXc, pl);
+  cudaFree(dXc);
+  if (rc) { bn_destroy(c); *out = nullptr; }
+  return rc;
+}
+
+extern "C" int bn_create_from_stats(int n_samples, int P, const double* mean, const double* centered,
+                                    const int* src, const int* tgt, int n_edges, const int* node_type,
+                                    int max_par, double phi, double omega, int device, bn_ctx** out) {
+  if (!mean || !centered) return fail(BN_ERR_BAD_ARG, "mean/centered_gram is NULL");
+  int rc = ctx_begin(n_samples, P, src, tgt, n_edges, node_type, max_par, phi, omega, device, out);
+  if (rc) { if (out && *out) { bn_destroy(*out); *out = nullptr; } return rc; }
+  bn_ctx* c = *out;
+  std::vector<double> colsum(P);
+  for (int p = 0; p < P; p++) colsum[p] = mean[p] * (double)n_samples;
+  cudaError_t e = cudaMemcpy(c->d_C, centered, (size_t)P * P * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_mean, mean, (size_t)P * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_colsum, colsum.data(), (size_t)P * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_diag(c->d_C, P, P, c->d_diag, c->stream);
+    c->launches++;
+    e = cudaStreamSynchronize(c->stream);
+  }
+  if (e != cudaSuccess) {
+    rc = fail(BN_ERR_CUDA, "upload of sufficient statistics: %s", cudaGetErrorString(e));
+    bn_destroy(c); *out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" int bn_set_stream(bn_ctx* c, void* s) {
+  if (!c) return fail(BN_ERR_BAD_ARG, "ctx is NULL");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return BN_OK;
+}
+
+extern "C" int bn_get_gram_ms(bn_ctx* c, float* ms) {
+  if (!c || !ms) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  *ms = c->gram_ms;
+  return BN_OK;
+}
+
+extern "C" int64_t bn_get_launch_count(bn_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int bn_get_stats(bn_ctx* c, double* sum_x, double* sum_xx, double* mean, double* centered) {
+  if (!c) return fail(BN_ERR_BAD_ARG, "ctx is NULL");
+  CU_TRY(cudaSetDevice(c->device));
+  const int P = c->P;
+  std::vector<double> C((size_t)P * P), cs(P), mu(P);
+  CU_TRY(cudaMemcpy(C.data(), c->d_C, C.size() * 8, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(cs.data(), c->d_colsum, (size_t)P * 8, cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemcpy(mu.data(), c->d_mean, (size_t)P * 8, cudaMemcpyDeviceToHost));
+  if (sum_x) memcpy(sum_x, cs.data(), (size_t)P * 8);
+  if (mean) memcpy(mean, mu.data(), (size_t)P * 8);
+  if (centered) memcpy(centered, C.data(), C.size() * 8);
+  if (sum_xx) {
+    // marshalling only: sum x_i x_j = C_ij + N mean_i mean_j (C is about the computed means)
+    const double n = (double)c->n_samples;
+    for (int a = 0; a < P; a++)
+      for (int b = 0; b < P; b++) sum_xx[(size_t)a + (size_t)b * P] = C[(size_t)a * P + b] + n * mu[a] * mu[b];
+  }
+  return BN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------
+extern "C" int bn_score_nodes(bn_ctx* c, int n_items, const int* child, const int* parents, const int* n_par,
+                              double* out_ll) {
+  if (!c || !child || !parents || !n_par || !out_ll) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  if (n_items <= 0) return BN_OK;
+  for (int i = 0; i < n_items; i++) {
+    if (child[i] < 0 || child[i] >= c->P) return fail(BN_ERR_BAD_ARG, "child[%d] out of range", i);
+    if (n_par[i] < 0 || n_par[i] > c->max_par) return fail(BN_ERR_BAD_ARG, "n_par[%d] out of range", i);
+    if (c->n_samples - n_par[i] - 1 <= 0) return fail(BN_ERR_BAD_ARG, "n_par[%d] leaves no degrees of freedom", i);
+    for (int e = 0; e < n_par[i]; e++) {
+      const int q = parents[(size_t)i * c->max_par + e];
+      if (q < 0 || q >= c->P) return fail(BN_ERR_BAD_ARG, "parents[%d][%d] out of range", i, e);
+    }
+  }
+  CU_TRY(cudaSetDevice(c->device));
+  int *d_child = nullptr, *d_par = nullptr, *d_np = nullptr, *d_npd = nullptr;
+  double* d_out = nullptr;
+  int rc = BN_OK;
+  cudaError_t e = cudaMalloc((void**)&d_child, (size_t)n_items * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_par, (size_t)n_items * c->max_par * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_np, (size_t)n_items * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_npd, 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)n_items * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_child, child, (size_t)n_items * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, parents, (size_t)n_items * c->max_par * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_np, n_par, (size_t)n_items * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_npd, 0, 4, c->stream);
+  if (e == cudaSuccess) {
+    const char* msg = launch_score_nodes(c->d_C, c->P, c->n_samples, c->max_par, n_items, d_child, d_par, d_np,
+                                         d_out, d_npd, c->stream);
+    c->launches++;
+    if (msg) rc = fail(BN_ERR_UNSUPPORTED, "%s", msg);
+  }
+  if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(out_ll, d_out, (size_t)n_items * 8, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? BN_ERR_OOM : BN_ERR_CUDA, "bn_score_nodes: %s", cudaGetErrorString(e));
+  cudaFree(d_child); cudaFree(d_par); cudaFree(d_np); cudaFree(d_npd); cudaFree(d_out);
+  return rc;
+}
+
+static int sweep_device(bn_ctx* c, int n_graphs, const int* d_parents, const int* d_npar, double* d_base,
+                        double* d_score, double* d_hr, float* kernel_ms) {
+  int *d_te = nullptr, *d_ag = nullptr;
+  CU_TRY(cudaMalloc((void**)&d_te, (size_t)n_graphs * 4));
+  cudaError_t e = cudaMalloc((void**)&d_ag, (size_t)n_graphs * 4);
+  if (e != cudaSuccess) { cudaFree(d_te); return fail(BN_ERR_OOM, "sweep scratch"); }
+  SweepParams sp;
+  sp.P = c->P; sp.max_par = c->max_par; sp.n_graphs = n_graphs; sp.n_samples = c->n_samples;
+  sp.n_sim_edges = c->n_sim_edges; sp.C = c->d_C; sp.ldc = c->P; sp.diag = c->d_diag;
+  sp.node_type = c->d_node_type; sp.sim_edge = c->d_sim_edge; sp.phi = c->phi; sp.omega = c->omega;
+  sp.parents = d_parents; sp.n_par = d_npar; sp.te = d_te; sp.agree = d_ag;
+  sp.out_base = d_base; sp.out_score = d_score; sp.out_log_hr = d_hr;
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, c->stream);
+  const char* msg = launch_sweep(sp, c->stream);
+  c->launches += 2;
+  cudaEventRecord(ev1, c->stream);
+  int rc = BN_OK;
+  if (msg) rc = fail(BN_ERR_UNSUPPORTED, "%s", msg);
+  e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess && !rc) rc = fail(BN_ERR_CUDA, "sweep kernel: %s", cudaGetErrorString(e));
+  if (!rc && kernel_ms) cudaEventElapsedTime(kernel_ms, ev0, ev1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  cudaFree(d_te); cudaFree(d_ag);
+  return rc;
+}
+
+extern "C" int bn_score_all_proposals_device(bn_ctx* c, int n_graphs, const int* d_parents, const int* d_npar,
+                                             double* d_base, double* d_score, double* d_hr, float* kernel_ms) {
+  if (!c || !d_parents || !d_npar) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  if (n_graphs <= 0) return fail(BN_ERR_BAD_ARG, "n_graphs <= 0");
+  CU_TRY(cudaSetDevice(c->device));
+  return sweep_device(c, n_graphs, d_parents, d_npar, d_base, d_score, d_hr, kernel_ms);
+}
+
+extern "C" int bn_score_all_proposals(bn_ctx* c, int n_graphs, const int* parents, const int* n_par,
+                                      double* out_base, double* out_score, double* out_log_hr) {
+  if (!c || !parents || !n_par) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  if (n_graphs <= 0) return fail(BN_ERR_BAD_ARG, "n_graphs <= 0");
+  const int P = c->P, MP = c->max_par;
+  for (int64_t i = 0; i < (int64_t)n_graphs * P; i++) {
+    if (n_par[i] < 0 || n_par[i] > MP) return fail(BN_ERR_BAD_ARG, "n_par[%lld] out of range", (long long)i);
+    for (int e = 0; e < n_par[i]; e++) {
+      const int q = parents[i * MP + e];
+      if (q < 0 || q >= P) return fail(BN_ERR_BAD_ARG, "parents[%lld][%d] out of range", (long long)i, e);
+    }
+  }
+  CU_TRY(cudaSetDevice(c->device));
+  const size_t npp = (size_t)n_graphs * P * P;
+  int *d_par = nullptr, *d_np = nullptr;
+  double *d_base = nullptr, *d_score = nullptr, *d_hr = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_par, (size_t)n_graphs * P * MP * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_np, (size_t)n_graphs * P * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_base, (size_t)n_graphs * P * 8);
+  if (e == cudaSuccess && out_score) e = cudaMalloc((void**)&d_score, npp * 8);
+  if (e == cudaSuccess && out_log_hr) e = cudaMalloc((void**)&d_hr, npp * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(d_par, parents, (size_t)n_graphs * P * MP * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_np, n_par, (size_t)n_graphs * P * 4, cudaMemcpyHostToDevice);
+  int rc = BN_OK;
+  if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? BN_ERR_OOM : BN_ERR_CUDA, "bn_score_all_proposals: %s", cudaGetErrorString(e));
+  if (!rc) rc = sweep_device(c, n_graphs, d_par, d_np, d_base, d_score, d_hr, nullptr);
+  if (!rc) {
+    if (out_base) e = cudaMemcpy(out_base, d_base, (size_t)n_graphs * P * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_score) e = cudaMemcpy(out_score, d_score, npp * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_log_hr) e = cudaMemcpy(out_log_hr, d_hr, npp * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "bn_score_all_proposals D2H: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_par); cudaFree(d_np); cudaFree(d_base); cudaFree(d_score); cudaFree(d_hr);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// chains
+// ---------------------------------------------------------------------------
+static uint64_t splitmix64(uint64_t& x) {
+  uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// R's set.seed() scrambling for the Mersenne-Twister (R sources, src/main/RNG.c: RNG_Init)
+static void rmt_seed_state(uint32_t seed, uint32_t* mt) {
+  for (int j = 0; j < 50; j++) seed = 69069u * seed + 1u;
+  for (int j = 0; j < 625; j++) {
+    seed = 69069u * seed + 1u;
+    if (j > 0) mt[j - 1] = seed;  // word 0 is the position (forced to 624)
+  }
+}
+
+struct DevBuf {  // frees on scope exit
+  std::vector<void*> ptrs;
+  ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T>
+  cudaError_t alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1);
+    if (e == cudaSuccess) ptrs.push_back((void*)*p);
+    return e;
+  }
+};
+
+extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* final_parents, int* final_n_par,
+                      bn_chain_stats* stats, float* kernel_ms) {
+  if (!c || !a || !trace) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  const int nc = a->n_chains;
+  if (nc <= 0) return fail(BN_ERR_BAD_ARG, "n_chains <= 0");
+  if (a->n_iter < 0 || a->output_every <= 0 || a->drop < 0) return fail(BN_ERR_BAD_ARG, "bad n_iter/output/drop");
+  if (a->initial_network == 1)
+    return fail(BN_ERR_UNSUPPORTED, "InitialNetwork=1 (random start) is undefined behaviour in the reference (src/network.h:151-157)");
+  if (a->initial_network != 0 && a->initial_network != 2) return fail(BN_ERR_BAD_ARG, "InitialNetwork must be 0 or 2");
+  if (a->rng_kind < BN_RNG_WH || a->rng_kind > BN_RNG_REPLAY) return fail(BN_ERR_BAD_ARG, "bad rng_kind");
+  if (a->rng_kind == BN_RNG_REPLAY && (!a->replay || a->replay_len <= 0)) return fail(BN_ERR_BAD_ARG, "replay buffer missing");
+  const int need = (a->n_iter + a->output_every - 1) / a->output_every;
+  if (trace->capacity < need) return fail(BN_ERR_CAPACITY, "trace capacity %d < %d rows", trace->capacity, need);
+  if (!trace->n_rows || !trace->iter || !trace->changed_node || !trace->movetype || !trace->global_ll ||
+      !trace->additions || !trace->deletions || !trace->fn || !trace->fp)
+    return fail(BN_ERR_BAD_ARG, "trace column pointer is NULL");
+  if (c->n_samples - c->max_par - 1 <= 0) return fail(BN_ERR_BAD_ARG, "n_samples <= max_par + 1");
+  CU_TRY(cudaSetDevice(c->device));
+
+  const int64_t P = c->P, MP = c->max_par, W = (P + 31) / 32;
+  const int64_t cap = trace->capacity > 0 ? trace->capacity : 1;
+  DevBuf buf;
+  ChainWorkspace w;
+  memset(&w, 0, sizeof(w));
+  int sort_n = 1;
+  while (sort_n < P) sort_n <<= 1;
+  w.sort_n = sort_n;
+  CU_TRY(buf.alloc(&w.par, (size_t)(nc * P * MP)));
+  CU_TRY(buf.alloc(&w.born, (size_t)(nc * P * MP)));
+  CU_TRY(buf.alloc(&w.npar, (size_t)(nc * P)));
+  CU_TRY(buf.alloc(&w.base, (size_t)(nc * P)));
+  CU_TRY(buf.alloc(&w.anc, (size_t)(nc * P * W)));
+  CU_TRY(buf.alloc(&w.anc_cnt, (size_t)(nc * P)));
+  CU_TRY(buf.alloc(&w.haspar, (size_t)(nc * W)));
+  CU_TRY(buf.alloc(&w.sortbuf, (size_t)nc * sort_n));
+  const bool dev_out = a->device_outputs != 0;
+  if (dev_out) {
+    w.t_iter = trace->iter; w.t_changed = trace->changed_node; w.t_movetype = trace->movetype;
+    w.t_gll = trace->global_ll; w.t_add = trace->additions; w.t_del = trace->deletions;
+    w.t_fn = trace->fn; w.t_fp = trace->fp;
+  } else {
+    CU_TRY(buf.alloc(&w.t_iter, (size_t)(nc * cap))); CU_TRY(buf.alloc(&w.t_changed, (size_t)(nc * cap)));
+    CU_TRY(buf.alloc(&w.t_movetype, (size_t)(nc * cap))); CU_TRY(buf.alloc(&w.t_gll, (size_t)(nc * cap)));
+    CU_TRY(buf.alloc(&w.t_add, (size_t)(nc * cap))); CU_TRY(buf.alloc(&w.t_del, (size_t)(nc * cap)));
+    CU_TRY(buf.alloc(&w.t_fn, (size_t)(nc * cap))); CU_TRY(buf.alloc(&w.t_fp, (size_t)(nc * cap)));
+  }
+  const int mcap = (a->moves && a->moves_capacity > 0) ? a->moves_capacity : 0;
+  if (mcap) {
+    if (dev_out) w.moves = a->moves;
+    else CU_TRY(buf.alloc(&w.moves, (size_t)nc * mcap * 4));
+  }
+  if (a->edge_freq) {
+    if (dev_out) w.edge_freq = a->edge_freq;
+    else CU_TRY(buf.alloc(&w.edge_freq, (size_t)(nc * P * P)));
+    CU_TRY(cudaMemsetAsync(w.edge_freq, 0, (size_t)(nc * P * P) * 4, c->stream));
+  }
+
+  // uniform streams
+  ChainRngArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.kind = a->rng_kind;
+  std::vector<int> seeds((size_t)3 * nc);
+  if (a->seeds) {
+    memcpy(seeds.data(), a->seeds, seeds.size() * sizeof(int));
+  } else {
+    for (int ch = 0; ch < nc; ch++) {
+      if (ch == 0) { seeds[0] = 10437; seeds[1] = 13568; seeds[2] = 30524; }  // random4f.h:19-21
+      else {
+        uint64_t st = 1234ull + (uint64_t)ch;
+        seeds[3 * ch + 0] = 1 + (int)(splitmix64(st) % 30268ull);
+        seeds[3 * ch + 1] = 1 + (int)(splitmix64(st) % 30306ull);
+        seeds[3 * ch + 2] = 1 + (int)(splitmix64(st) % 30322ull);
+      }
+    }
+  }
+  if (a->rng_kind == BN_RNG_WH) {
+    for (int ch = 0; ch < nc; ch++) {
+      const int* s = &seeds[3 * ch];
+      // the reference's own iz seed (30524, random4f.h:21) exceeds its modulus 30323; the LCG
+      // step reduces it, so anything in 1..65535 is a valid starting state
+      if (s[0] < 1 || s[0] > 65535 || s[1] < 1 || s[1] > 65535 || s[2] < 1 || s[2] > 65535)
+        return fail(BN_ERR_BAD_ARG, "Wichmann-Hill seeds of chain %d out of range 1..65535", ch);
+    }
+  }
+  int* d_seeds = nullptr;
+  CU_TRY(buf.alloc(&d_seeds, seeds.size()));
+  CU_TRY(cudaMemcpyAsync(d_seeds, seeds.data(), seeds.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  ra.seeds = d_seeds;
+  std::vector<uint32_t> mt;
+  if (a->rng_kind == BN_RNG_RMT) {
+    mt.resize((size_t)624 * nc);
+    for (int ch = 0; ch < nc; ch++) rmt_seed_state((uint32_t)seeds[3 * ch], &mt[(size_t)624 * ch]);
+    CU_TRY(buf.alloc(&ra.mt_states, mt.size()));
+    CU_TRY(cudaMemcpyAsync(ra.mt_states, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (a->rng_kind == BN_RNG_REPLAY) {
+    double* d_rep = nullptr;
+    CU_TRY(buf.alloc(&d_rep, (size_t)nc * a->replay_len));
+    CU_TRY(cudaMemcpyAsync(d_rep, a->replay, (size_t)nc * a->replay_len * 8, cudaMemcpyHostToDevice, c->stream));
+    ra.replay = d_rep;
+    ra.replay_len = a->replay_len;
+  }
+
+  ChainParams p;
+  p.P = (int)P; p.max_par = (int)MP; p.W = (int)W; p.n_samples = c->n_samples;
+  p.C = c->d_C; p.ldc = P; p.node_type = c->d_node_type; p.sim_edge = c->d_sim_edge;
+  p.n_sim_edges = c->n_sim_edges; p.phi = c->phi; p.omega = c->omega;
+  p.initial_network = a->initial_network; p.drop = a->drop; p.n_iter = a->n_iter;
+  p.output_every = a->output_every; p.trace_capacity = (int)cap; p.moves_capacity = mcap;
+  p.prior_par = c->d_prior_par; p.prior_npar = c->d_prior_npar;
+
+  ChainResult* d_res = nullptr;
+  CU_TRY(buf.alloc(&d_res, (size_t)nc));
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, c->stream);
+  const char* msg = launch_chains(p, w, ra, d_res, nc, c->stream);
+  c->launches++;
+  cudaEventRecord(ev1, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+  if (msg) return fail(BN_ERR_UNSUPPORTED, "%s", msg);
+  if (e != cudaSuccess) return fail(BN_ERR_CUDA, "chain kernel: %s", cudaGetErrorString(e));
+  if (kernel_ms) *kernel_ms = ms;
+
+  std::vector<ChainResult> res(nc);
+  CU_TRY(cudaMemcpy(res.data(), d_res, sizeof(ChainResult) * nc, cudaMemcpyDeviceToHost));
+  int rc = BN_OK;
+  std::vector<int> nrows(nc), nmoves(nc);
+  for (int ch = 0; ch < nc; ch++) {
+    nrows[ch] = res[ch].n_rows;
+    nmoves[ch] = res[ch].n_moves < mcap ? res[ch].n_moves : mcap;
+    if (stats) {
+      bn_chain_stats& s = stats[ch];
+      s.uniforms = res[ch].uniforms; s.valid_iters = res[ch].valid_iters;
+      for (int t = 0; t < 3; t++) { s.proposed[t] = res[ch].proposed[t]; s.reject[t] = res[ch].reject[t]; }
+      s.n_nonpd = res[ch].n_nonpd; s.total_edges = res[ch].total_edges; s.status = res[ch].status;
+      s.windows = res[ch].windows;
+      s.alg_bytes = res[ch].alg_bytes;
+    }
+    if (res[ch].status && !rc)
+      rc = fail(res[ch].status, "chain %d: no legal proposal within the uniform window (all candidate nodes are sources/full/sinks?)", ch);
+  }
+  const cudaMemcpyKind out_kind = dev_out ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
+  CU_TRY(cudaMemcpy(trace->n_rows, nrows.data(), (size_t)nc * 4, out_kind));
+  if (a->n_moves) CU_TRY(cudaMemcpy(a->n_moves, nmoves.data(), (size_t)nc * 4, out_kind));
+  if (!dev_out) {
+    const size_t n = (size_t)(nc * cap);
+    CU_TRY(cudaMemcpy(trace->iter, w.t_iter, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->changed_node, w.t_changed, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->movetype, w.t_movetype, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->global_ll, w.t_gll, n * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->additions, w.t_add, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->deletions, w.t_del, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->fn, w.t_fn, n * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(trace->fp, w.t_fp, n * 4, cudaMemcpyDeviceToHost));
+    if (mcap) CU_TRY(cudaMemcpy(a->moves, w.moves, (size_t)nc * mcap * 16, cudaMemcpyDeviceToHost));
+    if (a->edge_freq) CU_TRY(cudaMemcpy(a->edge_freq, w.edge_freq, (size_t)(nc * P * P) * 4, cudaMemcpyDeviceToHost));
+  }
+  const cudaMemcpyKind fin_kind = dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (final_parents) CU_TRY(cudaMemcpy(final_parents, w.par, (size_t)(nc * P * MP) * 4, fin_kind));
+  if (final_n_par) CU_TRY(cudaMemcpy(final_n_par, w.npar, (size_t)(nc * P) * 4, fin_kind));
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// host twin of main_fun (src/bayesnet_mcmc.cpp:27-72)
+// ---------------------------------------------------------------------------
+extern "C" int bn_main_fun(const double* X, int n_samples, int n_nodes, const int* graph_source,
+                           const int* graph_target, int n_edges, const int* graph_node_labels,
+                           const int* graph_node_type, int MaxPar, double phi, double omega,
+                           int InitialNetwork, int drop, int N, int output, int rng_kind, const int* seeds,
+                           int capacity, int* iter, int* ChangedNode, int* movetype, double* globalLL,
+                           int* additions, int* deletions, int* FN, int* FP) {
+  (void)graph_node_labels;  // accepted and unused, as in the reference (src/bayesnet_mcmc.cpp:30,42-43)
+  bn_ctx* c = nullptr;
+  int rc = bn_create(X, n_samples, n_nodes, graph_source, graph_target, n_edges, graph_node_type, MaxPar, phi,
+                     omega, 0, &c);
+  if (rc) return -rc;
+  bn_run_args a;
+  memset(&a, 0, sizeof(a));
+  a.n_chains = 1; a.rng_kind = rng_kind; a.seeds = seeds; a.initial_network = InitialNetwork;
+  a.drop = drop; a.n_iter = N; a.output_every = output;
+  int n_rows = 0;
+  bn_trace t;
+  t.capacity = capacity; t.n_rows = &n_rows; t.iter = iter; t.changed_node = ChangedNode; t.movetype = movetype;
+  t.global_ll = globalLL; t.additions = additions; t.deletions = deletions; t.fn = FN; t.fp = FP;
+  rc = bn_run(c, &a, &t, nullptr, nullptr, nullptr, nullptr);
+  bn_destroy(c);
+  return rc ? -rc : n_rows;
+}

@@ -1,0 +1,29 @@
+// Host-side interface of the Gram build (gram.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bn {
+
+constexpr int GRAM_MEAN_MAX_CHUNKS = 64;
+
+struct GramPlan {
+  int n_tiles;          // ceil(P / 128)
+  int n_pairs;          // upper-triangular tile pairs
+  int stages_total;     // ceil(N / 32) pipeline stages along the sample axis
+  int n_splits;         // split-K factor
+  int64_t items;        // CTAs = n_splits * n_pairs
+  int64_t workspace_bytes;
+  int64_t ld_centered;  // leading dimension of the centred copy (multiple of 16)
+};
+
+GramPlan gram_plan(int n_samples, int P, int n_sms);
+
+// Enqueues means -> centring -> DMMA Gram -> reduction on `stream`.
+// Returns nullptr on success or a static error string.
+const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, double* dXc,
+                       int64_t ld_centered, double* d_partial, const GramPlan& pl, double* d_colsum,
+                       double* d_mean, double* d_C, int64_t ldc, double* d_scratch_part,
+                       int* d_error_flag, cudaStream_t stream, int64_t* launches);
+
+}  // namespace bn

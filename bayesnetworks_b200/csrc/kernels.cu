@@ -1,0 +1,316 @@
+// K2 (batched proposal scoring), K3 (chains), K4 (node scores) -- device entry points.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "chain_core.cuh"
+#include "kernels.h"
+
+namespace bn {
+
+// ---------------------------------------------------------------------------
+// K3: one warp (= one CTA of 32 threads) per chain, persistent for the whole run.
+// Per-chain state lives in global memory and is served from this SM's L1 (only
+// this CTA touches it); the Gram is read with L2-only loads.
+// ---------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
+                                                   ChainResult* __restrict__ results) {
+  __shared__ double ubuf[RNG_CAP];
+  __shared__ WindowSlots ws;
+  const int ch = blockIdx.x;
+  const int64_t P = p.P, MP = p.max_par, W = p.W;
+
+  ChainMem m;
+  m.par = w.par + ch * P * MP;
+  m.npar = w.npar + ch * P;
+  m.born = w.born + ch * P * MP;
+  m.base = w.base + ch * P;
+  m.anc = w.anc + ch * P * W;
+  m.anc_cnt = w.anc_cnt + ch * P;
+  m.haspar = w.haspar + ch * W;
+  m.sortbuf = w.sortbuf + (int64_t)ch * w.sort_n;
+  const int64_t cap = p.trace_capacity;
+  m.t_iter = w.t_iter + ch * cap; m.t_changed = w.t_changed + ch * cap;
+  m.t_movetype = w.t_movetype + ch * cap; m.t_gll = w.t_gll + ch * cap;
+  m.t_add = w.t_add + ch * cap; m.t_del = w.t_del + ch * cap;
+  m.t_fn = w.t_fn + ch * cap; m.t_fp = w.t_fp + ch * cap;
+  m.moves = w.moves ? w.moves + (int64_t)ch * p.moves_capacity * 4 : nullptr;
+  m.edge_freq = w.edge_freq ? w.edge_freq + ch * P * P : nullptr;
+
+  RngStream rng;
+  if (ra.kind == RNG_WH)
+    rng_init_wh(rng, ra.seeds[3 * ch], ra.seeds[3 * ch + 1], ra.seeds[3 * ch + 2], ubuf);
+  else if (ra.kind == RNG_RMT)
+    rng_init_rmt(rng, ra.mt_states + (int64_t)ch * 624, ubuf);
+  else
+    rng_init_replay(rng, ra.replay + (int64_t)ch * ra.replay_len, ra.replay_len, ubuf);
+
+  ChainParams pp = p;
+  if (!m.moves) pp.moves_capacity = 0;
+  ChainScalars s;
+  run_chain<KMAX>(pp, m, s, rng, ws);
+
+  if (threadIdx.x == 0) {
+    ChainResult& r = results[ch];
+    r.uniforms = s.read_pos;
+    r.valid_iters = s.valid_iters;
+    r.alg_bytes = s.alg_bytes;
+    for (int t = 0; t < 3; t++) { r.proposed[t] = s.proposed[t]; r.reject[t] = s.reject[t]; }
+    r.n_nonpd = s.n_nonpd;
+    r.total_edges = s.te_true;
+    r.status = s.status;
+    r.windows = s.windows;
+    r.n_rows = s.n_rows;
+    r.n_moves = s.n_moves;
+  }
+}
+
+const char* launch_chains(const ChainParams& p, const ChainWorkspace& w, const ChainRngArgs& ra,
+                          ChainResult* d_results, int n_chains, cudaStream_t stream) {
+  if (p.max_par <= 8) chain_kernel<8><<<n_chains, 32, 0, stream>>>(p, w, ra, d_results);
+  else if (p.max_par <= 16) chain_kernel<16><<<n_chains, 32, 0, stream>>>(p, w, ra, d_results);
+  else if (p.max_par <= 64) chain_kernel<64><<<n_chains, 32, 0, stream>>>(p, w, ra, d_results);
+  else return "max_par > 64 is not supported";
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// K4: score(child | parent list) for explicit lists, one thread per item.
+// ---------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(128) score_nodes_kernel(const double* __restrict__ C, int64_t ldc,
+                                                          int n_samples, int max_par, int n_items,
+                                                          const int* __restrict__ child,
+                                                          const int* __restrict__ parents,
+                                                          const int* __restrict__ n_par,
+                                                          double* __restrict__ out, int* __restrict__ nonpd_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  double L[KMAX * (KMAX + 1) / 2], z[KMAX];
+  int S[KMAX];
+  const int k = n_par[i];
+  for (int e = 0; e < k; e++) S[e] = parents[(int64_t)i * max_par + e];
+  int npd = 0;
+  out[i] = score_set(C, ldc, child[i], S, k, n_samples, L, z, &npd);
+  if (npd) atomicAdd(nonpd_count, 1);
+}
+
+const char* launch_score_nodes(const double* C, int64_t ldc, int n_samples, int max_par, int n_items,
+                               const int* d_child, const int* d_parents, const int* d_npar, double* d_out,
+                               int* d_nonpd, cudaStream_t stream) {
+  const int grid = (n_items + 127) / 128;
+  if (max_par <= 8)
+    score_nodes_kernel<8><<<grid, 128, 0, stream>>>(C, ldc, n_samples, max_par, n_items, d_child, d_parents, d_npar, d_out, d_nonpd);
+  else if (max_par <= 16)
+    score_nodes_kernel<16><<<grid, 128, 0, stream>>>(C, ldc, n_samples, max_par, n_items, d_child, d_parents, d_npar, d_out, d_nonpd);
+  else if (max_par <= 64)
+    score_nodes_kernel<64><<<grid, 128, 0, stream>>>(C, ldc, n_samples, max_par, n_items, d_child, d_parents, d_npar, d_out, d_nonpd);
+  else return "max_par > 64 is not supported";
+  return nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// K2: every single-edge add/delete proposal of a DAG in one launch.
+// One warp per candidate parent set (graph g, child c): the warp gathers the
+// sub-Gram of the current parents S (+ the child's cross-covariances as an
+// augmented row) into shared memory, factorises it once (warp-parallel
+// right-looking Cholesky), then its lanes sweep the candidate parents j:
+//   add    j not in S: one more Cholesky row by forward substitution against the
+//          shared factor, O(k^2) -- the same arithmetic a fresh factorisation of
+//          S + [j] (push_back order, src/network.h:303) performs for its last row
+//   delete j in S:     fresh factorisation of S without j (erase order, :325)
+// Source/sink/max-parent masks (src/network.h:285,293) and the Potts prior
+// (src/network.h:254-279,334) are applied before the store.
+// Reads per add proposal: C[S_i][j] (k coalesced row segments), C[c][j], diag[j];
+// writes: score + log Hastings ratio.
+// ---------------------------------------------------------------------------
+__global__ void graph_counts_kernel(int P, int max_par, int n_graphs, const int* __restrict__ parents,
+                                    const int* __restrict__ n_par, const uint8_t* __restrict__ sim_edge,
+                                    int* __restrict__ te, int* __restrict__ agree) {
+  const int g = blockIdx.x;
+  if (g >= n_graphs) return;
+  int t = 0, a = 0;
+  for (int c = threadIdx.x; c < P; c += blockDim.x) {
+    const int k = n_par[(int64_t)g * P + c];
+    t += k;
+    for (int e = 0; e < k; e++)
+      a += sim_edge[(int64_t)parents[((int64_t)g * P + c) * max_par + e] + (int64_t)c * P] ? 1 : 0;
+  }
+  __shared__ int st[256], sa[256];
+  st[threadIdx.x] = t; sa[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { st[threadIdx.x] += st[threadIdx.x + o]; sa[threadIdx.x] += sa[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { te[g] = st[0]; agree[g] = sa[0]; }
+}
+
+// one more row of the factor for candidate j: w = L^-1 C[S,j]; returns the
+// updated (d_j, e_j) = (C_jj - w'w, C_jc - w'z)
+template <int KMAX>
+__device__ __forceinline__ void border_row(const double* __restrict__ C, int64_t ldc, const int* S, int k,
+                                           int j, const double* A, const double* zrow, double& dj,
+                                           double& ej) {
+  double w[KMAX];
+  if constexpr (KMAX <= 16) {
+    // fully unrolled with guards so that w[] stays in registers
+#pragma unroll
+    for (int i = 0; i < KMAX; i++) {
+      if (i < k) {
+        double acc = __ldcg(C + (int64_t)S[i] * ldc + j);
+        const double* Li = A + i * (i + 1) / 2;
+#pragma unroll
+        for (int t = 0; t < KMAX; t++)
+          if (t < i) acc -= Li[t] * w[t];
+        acc /= Li[i];
+        w[i] = acc;
+        dj -= acc * acc;
+        ej -= acc * zrow[i];
+      }
+    }
+  } else {
+    for (int i = 0; i < k; i++) {
+      double acc = __ldcg(C + (int64_t)S[i] * ldc + j);
+      const double* Li = A + i * (i + 1) / 2;
+      for (int t = 0; t < i; t++) acc -= Li[t] * w[t];
+      acc /= Li[i];
+      w[i] = acc;
+      dj -= acc * acc;
+      ej -= acc * zrow[i];
+    }
+  }
+}
+
+template <int KMAX, int SWEEP_WARPS>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp) {
+  constexpr int TRI = (KMAX + 1) * (KMAX + 2) / 2;  // augmented (k+1) lower triangle
+  __shared__ double sA[SWEEP_WARPS][TRI];
+  __shared__ int sS[SWEEP_WARPS][KMAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t wg = (int64_t)blockIdx.x * SWEEP_WARPS + warp;
+  const int P = sp.P, MP = sp.max_par;
+  if (wg >= (int64_t)sp.n_graphs * P) return;
+  const int g = (int)(wg / P), c = (int)(wg % P);
+  const int k = sp.n_par[wg];
+  const int* plist = sp.parents + wg * MP;
+  double* A = sA[warp];
+  int* S = sS[warp];
+  const double* __restrict__ C = sp.C;
+  const int64_t ldc = sp.ldc;
+
+  for (int e = lane; e < k; e += 32) S[e] = plist[e];
+  __syncwarp();
+  // gather: rows 0..k-1 = C[S_i][S_t] (t <= i); row k = C[S_t][c] (t < k), C[c][c]
+  const int tri = (k + 1) * (k + 2) / 2;
+  for (int idx = lane; idx < tri; idx += 32) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= idx) i++;
+    const int t = idx - i * (i + 1) / 2;
+    const int ri = (i < k) ? S[i] : c;
+    const int rt = (t < k) ? S[t] : c;
+    A[idx] = __ldcg(C + (int64_t)ri * ldc + rt);
+  }
+  __syncwarp();
+  const double Ccc = A[tri - 1];
+  // right-looking Cholesky over the first k columns; the augmented row k ends as
+  // (z_0 .. z_{k-1}, RSS)
+  bool pd = true;
+  for (int m = 0; m < k; m++) {
+    double d = A[m * (m + 1) / 2 + m];
+    if (!(d > 0.0)) { pd = false; break; }
+    d = sqrt(d);
+    __syncwarp();
+    if (lane == 0) A[m * (m + 1) / 2 + m] = d;
+    for (int i = m + 1 + lane; i <= k; i += 32) A[i * (i + 1) / 2 + m] /= d;
+    __syncwarp();
+    for (int i = m + 1 + lane; i <= k; i += 32) {
+      const double lim = A[i * (i + 1) / 2 + m];
+      for (int t = m + 1; t <= i; t++) A[i * (i + 1) / 2 + t] -= lim * A[t * (t + 1) / 2 + m];
+    }
+    __syncwarp();
+  }
+  const double n = (double)sp.n_samples;
+  const double syy = Ccc / (n - 1.0);
+  const double rss = A[tri - 1];
+  const double* zrow = A + k * (k + 1) / 2;
+  const double base = pd ? -(n / 2.0) * log((rss / (n - (double)k - 1.0)) / syy) : -INFINITY;
+  if (lane == 0 && sp.out_base) sp.out_base[wg] = base;
+
+  // prior bookkeeping of this graph
+  const int te = sp.te[g], ag = sp.agree[g];
+  const double old_prior = prior_value(sp.phi, sp.omega, (te - ag) + (sp.n_sim_edges - ag), te);
+  const uint8_t type_c = sp.node_type[c];
+  const bool can_add = (type_c != 1) && (k < MP);
+  const double nan = __longlong_as_double(0x7ff8000000000000ULL);
+  double* out_s = sp.out_score ? sp.out_score + wg * P : nullptr;
+  double* out_h = sp.out_log_hr ? sp.out_log_hr + wg * P : nullptr;
+
+  // ---- additions: lanes sweep j ----
+  for (int j0 = 0; j0 < P; j0 += 32) {
+    const int j = j0 + lane;
+    if (j >= P) break;
+    bool member = false;
+    for (int e = 0; e < k; e++) member |= (S[e] == j);
+    if (member) continue;  // deletions below
+    double sc = nan, hr = nan;
+    if (can_add && j != c && sp.node_type[j] != 2) {
+      if (!pd) {
+        sc = -INFINITY;
+      } else {
+        double dj = sp.diag[j];
+        double ej = __ldcg(C + (int64_t)c * ldc + j);
+        border_row<KMAX>(C, ldc, S, k, j, A, zrow, dj, ej);
+        if (dj > 0.0) {
+          const double rss_new = rss - ej * ej / dj;
+          sc = -(n / 2.0) * log((rss_new / (n - (double)k - 2.0)) / syy);
+        } else {
+          sc = -INFINITY;
+        }
+      }
+      const int a1 = sp.sim_edge[(int64_t)j + (int64_t)c * P] ? 1 : 0;
+      const int te_n = te + 1, ag_n = ag + a1;
+      const double new_prior = prior_value(sp.phi, sp.omega, (te_n - ag_n) + (sp.n_sim_edges - ag_n), te_n);
+      hr = sub_rn(add_rn(sub_rn(sc, base), new_prior), old_prior);
+    }
+    if (out_s) out_s[j] = sc;
+    if (out_h) out_h[j] = hr;
+  }
+  // ---- deletions: one lane per current parent ----
+  for (int e = lane; e < k; e += 32) {
+    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
+    int S2[KMAX];
+    int kk = 0;
+    for (int q = 0; q < k; q++) if (q != e) S2[kk++] = S[q];
+    int npd = 0;
+    const double sc = score_set(C, ldc, c, S2, kk, sp.n_samples, L, z, &npd);
+    const int j = S[e];
+    const int a1 = sp.sim_edge[(int64_t)j + (int64_t)c * P] ? 1 : 0;
+    const int te_n = te - 1, ag_n = ag - a1;
+    const double new_prior = prior_value(sp.phi, sp.omega, (te_n - ag_n) + (sp.n_sim_edges - ag_n), te_n);
+    if (out_s) out_s[j] = sc;
+    if (out_h) out_h[j] = sub_rn(add_rn(sub_rn(sc, base), new_prior), old_prior);
+  }
+}
+
+__global__ void diag_kernel(const double* __restrict__ C, int64_t ldc, int P, double* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) diag[i] = C[(int64_t)i * ldc + i];
+}
+
+void launch_diag(const double* C, int64_t ldc, int P, double* d_diag, cudaStream_t stream) {
+  diag_kernel<<<(P + 127) / 128, 128, 0, stream>>>(C, ldc, P, d_diag);
+}
+
+const char* launch_sweep(const SweepParams& sp, cudaStream_t stream) {
+  graph_counts_kernel<<<sp.n_graphs, 256, 0, stream>>>(sp.P, sp.max_par, sp.n_graphs, sp.parents, sp.n_par,
+                                                       sp.sim_edge, sp.te, sp.agree);
+  const int64_t warps = (int64_t)sp.n_graphs * sp.P;
+  if (sp.max_par <= 8) sweep_kernel<8, 4><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(sp);
+  else if (sp.max_par <= 16) sweep_kernel<16, 4><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(sp);
+  else if (sp.max_par <= 64) sweep_kernel<64, 2><<<(unsigned)((warps + 1) / 2), 64, 0, stream>>>(sp);
+  else return "max_par > 64 is not supported";
+  return nullptr;
+}
+
+}  // namespace bn

@@ -1,0 +1,51 @@
+// Host-side interface of kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "chain_core.cuh"
+
+namespace bn {
+
+struct ChainWorkspace {  // arrays over all chains of a run (device memory)
+  int* par; int* npar; int* born; double* base;
+  uint32_t* anc; int* anc_cnt; uint32_t* haspar;
+  unsigned long long* sortbuf; int sort_n;
+  int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
+  int* t_add; int* t_del; int* t_fn; int* t_fp;
+  int* moves; int* edge_freq;
+};
+
+struct ChainRngArgs {
+  int kind;
+  const int* seeds;          // [3*n_chains]
+  uint32_t* mt_states;       // [624*n_chains] (R-MT)
+  const double* replay;      // [replay_len*n_chains]
+  int64_t replay_len;
+};
+
+struct ChainResult {
+  int64_t uniforms, valid_iters, alg_bytes;
+  int proposed[3], reject[3];
+  int n_nonpd, total_edges, status, windows, n_rows, n_moves;
+};
+
+struct SweepParams {
+  int P, max_par, n_graphs, n_samples, n_sim_edges;
+  const double* C; int64_t ldc; const double* diag;
+  const uint8_t* node_type; const uint8_t* sim_edge;
+  double phi, omega;
+  const int* parents; const int* n_par;   // [g][P][max_par], [g][P]
+  int* te; int* agree;                     // [g] scratch
+  double* out_base; double* out_score; double* out_log_hr;
+};
+
+const char* launch_chains(const ChainParams& p, const ChainWorkspace& w, const ChainRngArgs& ra,
+                          ChainResult* d_results, int n_chains, cudaStream_t stream);
+const char* launch_score_nodes(const double* C, int64_t ldc, int n_samples, int max_par, int n_items,
+                               const int* d_child, const int* d_parents, const int* d_npar, double* d_out,
+                               int* d_nonpd, cudaStream_t stream);
+void launch_diag(const double* C, int64_t ldc, int P, double* d_diag, cudaStream_t stream);
+const char* launch_sweep(const SweepParams& sp, cudaStream_t stream);
+
+}  // namespace bn

@@ -1,0 +1,159 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the
+golden fixtures generated from the reference itself.  Bars (BASELINE.json north_star):
+integer trace columns, accepted-move sequence and edge set bit-identical; local LL and
+globalLL within 1e-9 relative (atol 1e-9 * N/2 for scores that are ~0)."""
+import numpy as np
+import pytest
+
+from conftest import centered_stats, prior_lists
+
+pytestmark = pytest.mark.gpu
+
+INT_COLS = ("iter", "ChangedNode", "movetype", "additions", "deletions", "FN", "FP")
+RTOL = 1e-9
+
+
+def ll_close(a, b, n_samples):
+    return np.allclose(a, b, rtol=RTOL, atol=RTOL * n_samples / 2)
+
+
+@pytest.fixture(scope="module")
+def ctx(dataset):
+    from bayesnetworks_b200 import Context
+    c = Context.from_data(dataset["X"], dataset["source"], dataset["target"], dataset["node_type"],
+                          max_par=50)
+    yield c
+    c.close()
+
+
+def test_gram_matches_reference_sums(ctx, dataset, golden):
+    sum_x, sum_xx, mean, centered = ctx.stats()
+    X = dataset["X"]
+    np.testing.assert_allclose(sum_x, golden["sumX"], rtol=1e-13)
+    np.testing.assert_allclose(sum_xx, golden["sumXX"], rtol=1e-12, atol=1e-9)
+    m, C = centered_stats(X)
+    np.testing.assert_allclose(mean, m, rtol=1e-13)
+    np.testing.assert_allclose(centered, C, rtol=1e-11, atol=1e-9)
+    assert np.array_equal(centered, centered.T)
+
+
+def test_scores_prior_dag(ctx, dataset, golden):
+    P = dataset["X"].shape[1]
+    par, npar = prior_lists(dataset["source"], dataset["target"], P, 50)
+    got = ctx.score_nodes(np.arange(P), par, npar)
+    assert ll_close(got, golden["prior_scores"], 2000)
+    assert abs(got.sum() - float(golden["prior_globalLL"])) <= RTOL * float(golden["prior_globalLL"])
+    got0 = ctx.score_nodes(np.arange(P), np.full((P, 50), -1), np.zeros(P))
+    assert ll_close(got0, golden["null_scores"], 2000)
+
+
+def test_scores_random_parent_sets(ctx, dataset, oracle):
+    X = dataset["X"]
+    N, P = X.shape
+    rng = np.random.default_rng(5)
+    stats = oracle.gram(X)
+    items = 300
+    child = rng.integers(0, P, items)
+    npar = rng.integers(0, 9, items)
+    par = np.full((items, 50), -1, np.int32)
+    want = np.zeros(items)
+    for i in range(items):
+        cand = [q for q in rng.permutation(P) if q != child[i]][: npar[i]]
+        par[i, : npar[i]] = cand
+        want[i], _ = oracle.score(X, child[i], cand, stats=stats)
+    got = ctx.score_nodes(child, par, npar)
+    assert ll_close(got, want, N)
+
+
+@pytest.mark.parametrize("name,rng,seed", [("cfg1", "rmt", 1234), ("cfg2", "wh", None)])
+def test_chain_bit_identical_to_reference(ctx, golden, name, rng, seed):
+    res, _ = ctx.run(n_chains=1, n_iter=50000, output=100, rng=rng, seeds=seed, log_moves=True)
+    r = res[0]
+    for k in INT_COLS:
+        assert np.array_equal(r.trace[k], golden[f"{name}_{k}"]), k
+    assert ll_close(r.trace["globalLL"], golden[f"{name}_globalLL"], 2000)
+    assert r.uniforms == int(golden[f"{name}_uniforms"])
+    assert np.array_equal(r.accepted_moves, golden[f"{name}_accepted_moves"])
+    assert np.array_equal(np.asarray(r.edges(), np.int32), golden[f"{name}_final_edges"])
+    assert list(r.proposed) == list(golden[f"{name}_proposed"])
+    assert list(r.reject) == list(golden[f"{name}_reject"])
+
+
+def test_chain_every_iteration(dataset, golden):
+    from bayesnetworks_b200 import Context
+    with Context.from_data(dataset["X"], dataset["source"], dataset["target"], dataset["node_type"],
+                           max_par=8) as c:
+        r = c.run(n_iter=4000, output=1, rng="wh")[0][0]
+        for k in INT_COLS:
+            assert np.array_equal(r.trace[k], golden[f"every_wh_{k}"]), k
+        assert ll_close(r.trace["globalLL"], golden["every_wh_globalLL"], 2000)
+        r = c.run(n_iter=2000, output=1, rng="rmt", seeds=99, initial_network=0)[0][0]
+        for k in INT_COLS:
+            assert np.array_equal(r.trace[k], golden[f"every_init0_{k}"]), k
+        assert ll_close(r.trace["globalLL"], golden["every_init0_globalLL"], 2000)
+
+
+def test_main_fun_c_abi(dataset, golden):
+    from bayesnetworks_b200 import create_network, bn_mcmc, Network
+    g = Network(source=dataset["source"], target=dataset["target"], node_labels=list(range(81)),
+                node_type=[("neither", "source", "sink")[t] for t in dataset["node_type"]])
+    out = bn_mcmc(dataset["X"], g, N=5000, rng="rmt", seed=1234)
+    assert list(out.keys()) == ["iter", "ChangedNode", "movetype", "globalLL", "additions",
+                                "deletions", "FN", "FP"]
+    n = len(out["iter"])
+    assert n == 50
+    for k in INT_COLS:
+        assert np.array_equal(out[k], golden[f"cfg1_{k}"][:n]), k
+    assert ll_close(out["globalLL"], golden["cfg1_globalLL"][:n], 2000)
+
+
+def test_sweep_matches_oracle(ctx, dataset, oracle, golden):
+    X = dataset["X"]
+    N, P = X.shape
+    MP = 50
+    par, npar = prior_lists(dataset["source"], dataset["target"], P, MP)
+    base, score, hr = ctx.score_all_proposals(par, npar)
+    assert ll_close(base[0], golden["prior_scores"], N)
+    stats = oracle.gram(X)
+    nt = dataset["node_type"]
+    sim = np.zeros((P, P), bool)
+    for s, t in zip(dataset["source"], dataset["target"]):
+        sim[t - 1, s - 1] = True
+    te = int(npar.sum())
+    rng = np.random.default_rng(11)
+    checked = 0
+    for c in list(rng.permutation(P)[:12]) + [0, 21, 22]:
+        cur = list(par[c, : npar[c]])
+        for j in range(P):
+            got = score[0, c, j]
+            if j in cur:
+                new = [q for q in cur if q != j]
+                want, _ = oracle.score(X, c, new, stats=stats)
+                dte, dag = -1, -int(sim[c, j])
+            else:
+                if j == c or nt[c] == 1 or nt[j] == 2 or len(cur) >= MP:
+                    assert np.isnan(got) and np.isnan(hr[0, c, j])
+                    continue
+                want, _ = oracle.score(X, c, cur + [j], stats=stats)
+                dte, dag = 1, int(sim[c, j])
+            assert ll_close(got, want, N), (c, j, got, want)
+            ag = te  # prior DAG: every edge agrees
+            old_prior = -1.0 * ((te - ag) + (44 - ag)) - 6.9 * te
+            te2, ag2 = te + dte, ag + dag
+            new_prior = -1.0 * ((te2 - ag2) + (44 - ag2)) - 6.9 * te2
+            want_hr = (want - golden["prior_scores"][c]) + new_prior - old_prior
+            assert abs(hr[0, c, j] - want_hr) <= 1e-9 * max(1.0, abs(want_hr)) + 1e-6
+            checked += 1
+    assert checked > 500
+
+
+def test_multichain_invariance(ctx, golden):
+    """Chain c's trajectory depends only on its own seeds, not on how many chains run."""
+    res8, _ = ctx.run(n_chains=8, n_iter=3000, output=100, rng="wh")
+    res1, _ = ctx.run(n_chains=1, n_iter=3000, output=100, rng="wh")
+    for k in INT_COLS:
+        assert np.array_equal(res8[0].trace[k], res1[0].trace[k])
+        assert np.array_equal(res8[0].trace[k], golden[f"cfg2_{k}"][:30])
+    assert np.array_equal(res8[0].trace["globalLL"], res1[0].trace["globalLL"])
+    # distinct seeds -> distinct trajectories
+    assert not np.array_equal(res8[1].trace["ChangedNode"], res8[0].trace["ChangedNode"])
