@@ -49,6 +49,12 @@ class ChainResult:
                 for c in range(len(self.final_npar)) for e in range(int(self.final_npar[c]))]
 
 
+def set_default_stream(cuda_stream: Optional[int]) -> None:
+    """Contexts created afterwards by this thread launch on ``cuda_stream`` (a raw
+    ``cudaStream_t`` value, e.g. ``torch.cuda.current_stream().cuda_stream``); None resets."""
+    check(_lib.lib().bn_set_default_stream(C.c_void_p(cuda_stream or 0)))
+
+
 class Context:
     """Device-resident sufficient statistics + prior graph (``bn_ctx``)."""
 
@@ -249,9 +255,7 @@ class Context:
             for k in ("additions", "deletions", "FN", "FP"):
                 trace[k] = ints[k][ch, :r].copy()
             s = stats[ch]
-            fp_ch = fpar[ch].copy()
-            for c_ in range(p):
-                fp_ch[c_, fnpar[ch, c_]:] = -1
+            fp_ch = np.where(np.arange(mp)[None, :] < fnpar[ch][:, None], fpar[ch], -1).astype(np.int32)
             out.append(ChainResult(
                 trace=trace, uniforms=int(s.uniforms), valid_iters=int(s.valid_iters),
                 proposed=tuple(s.proposed), reject=tuple(s.reject), n_nonpd=int(s.n_nonpd),

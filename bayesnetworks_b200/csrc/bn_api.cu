@@ -36,12 +36,83 @@ static int fail(int code, const char* fmt, ...) {
                   #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                       \
   } while (0)
 
+static thread_local cudaStream_t g_default_stream = nullptr;
+
 extern "C" const char* bn_last_error(void) { return g_err; }
+extern "C" int bn_set_default_stream(void* s) { g_default_stream = (cudaStream_t)s; return BN_OK; }
 extern "C" int bn_abi_version(void) { return BN_B200_ABI_VERSION; }
 extern "C" int bn_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
+}
+
+// ---------------------------------------------------------------------------
+// device workspace pool: cudaMalloc/cudaFree of the 100 MB..GB scratch buffers (centred
+// copy of X, split-K partials, per-chain state) costs far more than the kernels that use
+// them, so freed blocks are kept per device and handed out again.  bn_trim_pool() or
+// BN_B200_POOL=0 returns the memory to the driver.
+// ---------------------------------------------------------------------------
+#include <mutex>
+namespace {
+struct PoolBlock { void* p; size_t n; int dev; bool used; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool;
+const size_t kPoolMaxBlock = (size_t)8 << 30;
+
+bool pool_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("BN_B200_POOL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+
+cudaError_t pool_alloc(void** out, size_t n) {
+  if (n == 0) n = 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (pool_enabled()) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); i++) {
+      PoolBlock& b = g_pool[i];
+      if (!b.used && b.dev == dev && b.n >= n && b.n <= 2 * n + (1 << 20) &&
+          (best < 0 || b.n < g_pool[best].n))
+        best = i;
+    }
+    if (best >= 0) { g_pool[best].used = true; *out = g_pool[best].p; return cudaSuccess; }
+  }
+  cudaError_t e = cudaMalloc(out, n);
+  if (e != cudaSuccess && pool_enabled()) {
+    // out of memory: drop the cached blocks of this device and retry once
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    cudaGetLastError();
+    for (auto it = g_pool.begin(); it != g_pool.end();)
+      if (!it->used && it->dev == dev) { cudaFree(it->p); it = g_pool.erase(it); } else ++it;
+    e = cudaMalloc(out, n);
+  }
+  if (e == cudaSuccess && pool_enabled() && n <= kPoolMaxBlock) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.push_back({*out, n, dev, true});
+  }
+  return e;
+}
+
+void pool_free(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (PoolBlock& b : g_pool)
+      if (b.p == p) { b.used = false; return; }
+  }
+  cudaFree(p);
+}
+}  // namespace
+
+extern "C" int bn_trim_pool(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (auto it = g_pool.begin(); it != g_pool.end();)
+    if (!it->used) { cudaSetDevice(it->dev); cudaFree(it->p); it = g_pool.erase(it); } else ++it;
+  return BN_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -69,7 +140,7 @@ struct bn_ctx {
 
 template <typename T>
 static cudaError_t dalloc(bn_ctx* c, T** p, size_t n) {
-  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1);
+  cudaError_t e = pool_alloc((void**)p, n * sizeof(T));
   if (e == cudaSuccess && c) c->owned.push_back((void*)*p);
   return e;
 }
@@ -77,7 +148,7 @@ static cudaError_t dalloc(bn_ctx* c, T** p, size_t n) {
 extern "C" void bn_destroy(bn_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  for (void* p : c->owned) cudaFree(p);
+  for (void* p : c->owned) pool_free(p);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -117,7 +188,7 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sms = prop.multiProcessorCount;
   *out = c;  // from here on the caller destroys on failure
   CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  c->stream = c->own_stream;
+  c->stream = g_default_stream ? g_default_stream : c->own_stream;
 
   // parent lists edges[tgt-1].push_back(src-1), src/network.h:117-120
   std::vector<int> par((size_t)P * max_par, -1), npar(P, 0);
@@ -152,9 +223,9 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
 static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc, const GramPlan& pl) {
   double *d_partial = nullptr, *d_scratch = nullptr;
   int* d_flag = nullptr;
-  CU_TRY(cudaMalloc((void**)&d_partial, (size_t)pl.workspace_bytes));
-  cudaError_t e1 = cudaMalloc((void**)&d_scratch, (size_t)c->P * GRAM_MEAN_MAX_CHUNKS * sizeof(double));
-  cudaError_t e2 = cudaMalloc((void**)&d_flag, sizeof(int));
+  CU_TRY(pool_alloc((void**)&d_partial, (size_t)pl.workspace_bytes));
+  cudaError_t e1 = pool_alloc((void**)&d_scratch, (size_t)c->P * GRAM_MEAN_MAX_CHUNKS * sizeof(double));
+  cudaError_t e2 = pool_alloc((void**)&d_flag, sizeof(int));
   int rc = BN_OK;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(BN_ERR_OOM, "gram scratch allocation failed");
@@ -181,7 +252,7 @@ static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc,
   }
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
-  cudaFree(d_partial); cudaFree(d_scratch); cudaFree(d_flag);
+  pool_free(d_partial); pool_free(d_scratch); pool_free(d_flag);
   return rc;
 }
 
@@ -194,14 +265,14 @@ extern "C" int bn_create(const double* X, int n_samples, int P, const int* src, 
   bn_ctx* c = *out;
   const GramPlan pl = gram_plan(n_samples, P, c->n_sms);
   double* dXc = nullptr;
-  cudaError_t e = cudaMalloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
+  cudaError_t e = pool_alloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
   if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the device copy of X"); }
   // column p of the R matrix is contiguous: one pitched copy into the padded buffer
   e = cudaMemcpy2DAsync(dXc, (size_t)pl.ld_centered * 8, X, (size_t)n_samples * 8, (size_t)n_samples * 8,
                         (size_t)P, cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "H2D copy of X: %s", cudaGetErrorString(e));
   if (!rc) rc = ctx_build_gram(c, dXc, pl.ld_centered, dXc, pl);  // centred in place
-  cudaFree(dXc);
+  pool_free(dXc);
   if (rc) { bn_destroy(c); *out = nullptr; }
   return rc;
 }
@@ -216,10 +287,10 @@ extern "C" int bn_create_from_device(const double* dX, int64_t ld, int n_samples
   bn_ctx* c = *out;
   const GramPlan pl = gram_plan(n_samples, P, c->n_sms);
   double* dXc = nullptr;
-  cudaError_t e = cudaMalloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
+  cudaError_t e = pool_alloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
   if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the centred copy of X"); }
   rc = ctx_build_gram(c, dX, ld, dXc, pl);
-  cudaFree(dXc);
+  pool_free(dXc);
   if (rc) { bn_destroy(c); *out = nullptr; }
   return rc;
 }
@@ -302,11 +373,11 @@ extern "C" int bn_score_nodes(bn_ctx* c, int n_items, const int* child, const in
   int *d_child = nullptr, *d_par = nullptr, *d_np = nullptr, *d_npd = nullptr;
   double* d_out = nullptr;
   int rc = BN_OK;
-  cudaError_t e = cudaMalloc((void**)&d_child, (size_t)n_items * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_par, (size_t)n_items * c->max_par * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_np, (size_t)n_items * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_npd, 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, (size_t)n_items * 8);
+  cudaError_t e = pool_alloc((void**)&d_child, (size_t)n_items * 4);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_par, (size_t)n_items * c->max_par * 4);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_np, (size_t)n_items * 4);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_npd, 4);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_out, (size_t)n_items * 8);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_child, child, (size_t)n_items * 4, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_par, parents, (size_t)n_items * c->max_par * 4, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_np, n_par, (size_t)n_items * 4, cudaMemcpyHostToDevice, c->stream);
@@ -320,16 +391,16 @@ extern "C" int bn_score_nodes(bn_ctx* c, int n_items, const int* child, const in
   if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(out_ll, d_out, (size_t)n_items * 8, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) rc = fail(e == cudaErrorMemoryAllocation ? BN_ERR_OOM : BN_ERR_CUDA, "bn_score_nodes: %s", cudaGetErrorString(e));
-  cudaFree(d_child); cudaFree(d_par); cudaFree(d_np); cudaFree(d_npd); cudaFree(d_out);
+  pool_free(d_child); pool_free(d_par); pool_free(d_np); pool_free(d_npd); pool_free(d_out);
   return rc;
 }
 
 static int sweep_device(bn_ctx* c, int n_graphs, const int* d_parents, const int* d_npar, double* d_base,
                         double* d_score, double* d_hr, float* kernel_ms) {
   int *d_te = nullptr, *d_ag = nullptr;
-  CU_TRY(cudaMalloc((void**)&d_te, (size_t)n_graphs * 4));
-  cudaError_t e = cudaMalloc((void**)&d_ag, (size_t)n_graphs * 4);
-  if (e != cudaSuccess) { cudaFree(d_te); return fail(BN_ERR_OOM, "sweep scratch"); }
+  CU_TRY(pool_alloc((void**)&d_te, (size_t)n_graphs * 4));
+  cudaError_t e = pool_alloc((void**)&d_ag, (size_t)n_graphs * 4);
+  if (e != cudaSuccess) { pool_free(d_te); return fail(BN_ERR_OOM, "sweep scratch"); }
   SweepParams sp;
   sp.P = c->P; sp.max_par = c->max_par; sp.n_graphs = n_graphs; sp.n_samples = c->n_samples;
   sp.n_sim_edges = c->n_sim_edges; sp.C = c->d_C; sp.ldc = c->P; sp.diag = c->d_diag;
@@ -349,7 +420,7 @@ static int sweep_device(bn_ctx* c, int n_graphs, const int* d_parents, const int
   if (e != cudaSuccess && !rc) rc = fail(BN_ERR_CUDA, "sweep kernel: %s", cudaGetErrorString(e));
   if (!rc && kernel_ms) cudaEventElapsedTime(kernel_ms, ev0, ev1);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-  cudaFree(d_te); cudaFree(d_ag);
+  pool_free(d_te); pool_free(d_ag);
   return rc;
 }
 
@@ -377,11 +448,11 @@ extern "C" int bn_score_all_proposals(bn_ctx* c, int n_graphs, const int* parent
   const size_t npp = (size_t)n_graphs * P * P;
   int *d_par = nullptr, *d_np = nullptr;
   double *d_base = nullptr, *d_score = nullptr, *d_hr = nullptr;
-  cudaError_t e = cudaMalloc((void**)&d_par, (size_t)n_graphs * P * MP * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_np, (size_t)n_graphs * P * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_base, (size_t)n_graphs * P * 8);
-  if (e == cudaSuccess && out_score) e = cudaMalloc((void**)&d_score, npp * 8);
-  if (e == cudaSuccess && out_log_hr) e = cudaMalloc((void**)&d_hr, npp * 8);
+  cudaError_t e = pool_alloc((void**)&d_par, (size_t)n_graphs * P * MP * 4);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_np, (size_t)n_graphs * P * 4);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_base, (size_t)n_graphs * P * 8);
+  if (e == cudaSuccess && out_score) e = pool_alloc((void**)&d_score, npp * 8);
+  if (e == cudaSuccess && out_log_hr) e = pool_alloc((void**)&d_hr, npp * 8);
   if (e == cudaSuccess) e = cudaMemcpy(d_par, parents, (size_t)n_graphs * P * MP * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_np, n_par, (size_t)n_graphs * P * 4, cudaMemcpyHostToDevice);
   int rc = BN_OK;
@@ -393,7 +464,7 @@ extern "C" int bn_score_all_proposals(bn_ctx* c, int n_graphs, const int* parent
     if (e == cudaSuccess && out_log_hr) e = cudaMemcpy(out_log_hr, d_hr, npp * 8, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "bn_score_all_proposals D2H: %s", cudaGetErrorString(e));
   }
-  cudaFree(d_par); cudaFree(d_np); cudaFree(d_base); cudaFree(d_score); cudaFree(d_hr);
+  pool_free(d_par); pool_free(d_np); pool_free(d_base); pool_free(d_score); pool_free(d_hr);
   return rc;
 }
 
@@ -418,10 +489,10 @@ static void rmt_seed_state(uint32_t seed, uint32_t* mt) {
 
 struct DevBuf {  // frees on scope exit
   std::vector<void*> ptrs;
-  ~DevBuf() { for (void* p : ptrs) cudaFree(p); }
+  ~DevBuf() { for (void* p : ptrs) pool_free(p); }
   template <typename T>
   cudaError_t alloc(T** p, size_t n) {
-    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 1);
+    cudaError_t e = pool_alloc((void**)p, n * sizeof(T));
     if (e == cudaSuccess) ptrs.push_back((void*)*p);
     return e;
   }
@@ -451,17 +522,14 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   DevBuf buf;
   ChainWorkspace w;
   memset(&w, 0, sizeof(w));
-  int sort_n = 1;
-  while (sort_n < P) sort_n <<= 1;
-  w.sort_n = sort_n;
+  w.scratch_n = 4 * scratch_stride((int)P);
   CU_TRY(buf.alloc(&w.par, (size_t)(nc * P * MP)));
   CU_TRY(buf.alloc(&w.born, (size_t)(nc * P * MP)));
   CU_TRY(buf.alloc(&w.npar, (size_t)(nc * P)));
   CU_TRY(buf.alloc(&w.base, (size_t)(nc * P)));
-  CU_TRY(buf.alloc(&w.anc, (size_t)(nc * P * W)));
-  CU_TRY(buf.alloc(&w.anc_cnt, (size_t)(nc * P)));
+  CU_TRY(buf.alloc(&w.anc, (size_t)(nc * P * anc_stride((int)W))));
   CU_TRY(buf.alloc(&w.haspar, (size_t)(nc * W)));
-  CU_TRY(buf.alloc(&w.sortbuf, (size_t)nc * sort_n));
+  CU_TRY(buf.alloc(&w.scratch, (size_t)nc * w.scratch_n));
   const bool dev_out = a->device_outputs != 0;
   if (dev_out) {
     w.t_iter = trace->iter; w.t_changed = trace->changed_node; w.t_movetype = trace->movetype;
@@ -531,7 +599,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   }
 
   ChainParams p;
-  p.P = (int)P; p.max_par = (int)MP; p.W = (int)W; p.n_samples = c->n_samples;
+  p.P = (int)P; p.max_par = (int)MP; p.W = (int)W; p.Ws = anc_stride((int)W); p.n_samples = c->n_samples;
   p.C = c->d_C; p.ldc = P; p.node_type = c->d_node_type; p.sim_edge = c->d_sim_edge;
   p.n_sim_edges = c->n_sim_edges; p.phi = c->phi; p.omega = c->omega;
   p.initial_network = a->initial_network; p.drop = a->drop; p.n_iter = a->n_iter;

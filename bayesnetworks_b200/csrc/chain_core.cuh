@@ -31,7 +31,7 @@ namespace bn {
 constexpr int WIN = 32;  // speculative window (iterations), one lane each
 
 struct ChainParams {  // read-only, shared by all chains of a run
-  int P, max_par, W, n_samples;
+  int P, max_par, W, Ws, n_samples;  // W = words per bitset, Ws = row stride of anc (odd when in smem)
   const double* C;      // centred Gram [P][ldc]
   int64_t ldc;
   const uint8_t* node_type;  // [P] 0 neither / 1 source / 2 sink
@@ -50,10 +50,9 @@ struct ChainMem {  // per-chain global memory
   int* npar;           // [P]
   int* born;           // [P][max_par] first counted iteration of the edge (tabulation)
   double* base;        // [P] score of each node under the current graph
-  uint32_t* anc;       // [P][W] ancestor bitsets
-  int* anc_cnt;        // [P] popcount of anc rows (topological key)
+  uint32_t* anc;       // [P][Ws] ancestor bitsets
   uint32_t* haspar;    // [W] nodes with >= 1 parent
-  unsigned long long* sortbuf;  // [pow2 >= P] scratch for the ancestor rebuild
+  int* scratch;        // [4 * scratch_stride(P)] lists / keys / histogram for the ancestor updates
   // outputs
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
   int* t_add; int* t_del; int* t_fn; int* t_fp;
@@ -120,121 +119,193 @@ BN_HD int select_kth(const uint32_t* bits, int W, int k) {
 }
 
 // ---------------------------------------------------------------------------
-// Ancestor bitsets
+// Ancestor bitsets.  Row d = ancestors of node d, Ws words apart (Ws % 4 == 0, 16 B
+// aligned), processed in 128-bit chunks: `lpr` lanes share one row, so a warp updates
+// `rpp` = 32/lpr rows per pass (4 rows for 1,000 nodes).
 // ---------------------------------------------------------------------------
+struct alignas(16) U4 { uint32_t x, y, z, w; };
+BN_HD U4 or4(U4 a, U4 b) { U4 r; r.x = a.x | b.x; r.y = a.y | b.y; r.z = a.z | b.z; r.w = a.w | b.w; return r; }
+BN_HD bool ne4(U4 a, U4 b) { return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0u; }
+BN_HD int popc4(U4 a) { return popc32(a.x) + popc32(a.y) + popc32(a.z) + popc32(a.w); }
+BN_HD U4 with_bit(U4 v, int b) {  // set bit b (0..127) of the chunk
+  const uint32_t m = 1u << (b & 31);
+  const int w = b >> 5;
+  v.x |= (w == 0) ? m : 0u; v.y |= (w == 1) ? m : 0u; v.z |= (w == 2) ? m : 0u; v.w |= (w == 3) ? m : 0u;
+  return v;
+}
+
+struct RowGeom { int chunks, lpr, rpp; };
+BN_HD RowGeom row_geom(const ChainParams& p) {
+  RowGeom g;
+  g.chunks = (p.W + 3) / 4;
+  g.lpr = 1;
+  while (g.lpr < g.chunks && g.lpr < Warp::NL) g.lpr <<= 1;
+  g.rpp = Warp::NL / g.lpr;
+  return g;
+}
+
+BN_HD int group_sum(int v, int lpr) {  // sum over the lpr lanes that share a row
+#if defined(__CUDA_ARCH__)
+  for (int o = 1; o < lpr; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#else
+  (void)lpr;
+#endif
+  return v;
+}
+
+BN_HD int atomic_fetch_inc(int* p) {
+#if defined(__CUDA_ARCH__)
+  return atomicAdd(p, 1);
+#else
+  return (*p)++;
+#endif
+}
+
+// scratch layout: four int arrays of P32 entries
+BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 32; }
+
+// nodes that have c as an ancestor (ascending), optionally preceded by c itself
+BN_HD int collect_desc(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list) {
+  const int l = Warp::lane(), P = p.P;
+  int n = 0;
+  for (int d0 = 0; d0 < P; d0 += Warp::NL) {
+    const int d = d0 + l;
+    const int flag = (d < P) && ((include_self && d == c) || test_bit(m.anc + (int64_t)d * p.Ws, c));
+    const uint32_t mask = Warp::ballot(flag);
+    if (flag) list[n + popc32(mask & ((1u << l) - 1u))] = d;
+    n += popc32(mask);
+  }
+  Warp::sync();
+  return n;
+}
+
+// anc[d] = union over the parents q of d of (anc[q] u {q}); all lanes, one row
+BN_HD void recompute_row(const ChainParams& p, ChainMem& m, int d, int chunks) {
+  U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
+  const int* pd = m.par + (int64_t)d * p.max_par;
+  const int kd = m.npar[d];
+  for (int ch = Warp::lane(); ch < chunks; ch += Warp::NL) {
+    U4 v = {0u, 0u, 0u, 0u};
+    for (int e = 0; e < kd; e++) {
+      const int q = pd[e];
+      v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
+      if (ch == (q >> 7)) v = with_bit(v, q & 127);
+    }
+    ad[ch] = v;
+  }
+}
 
 // after adding parent j to child c: every node in {c} u desc(c) gains anc[j] u {j}
 BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
-  const int l = Warp::lane(), W = p.W, P = p.P;
-  const uint32_t* aj = m.anc + (int64_t)j * W;
-  for (int d0 = 0; d0 < P; d0 += Warp::NL) {
-    const int d = d0 + l;
-    const int flag = (d < P) && (d == c || test_bit(m.anc + (int64_t)d * W, c));
-    uint32_t mask = Warp::ballot(flag);
-    while (mask) {
-      const int b = ffs32(mask) - 1;
-      mask &= mask - 1;
-      uint32_t* ad = m.anc + (int64_t)(d0 + b) * W;
-      int cnt = 0;
-      for (int w = l; w < W; w += Warp::NL) {
-        uint32_t v = ad[w] | aj[w];
-        if (w == (j >> 5)) v |= 1u << (j & 31);
-        ad[w] = v;
-        cnt += popc32(v);
+  const RowGeom g = row_geom(p);
+  const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr;
+  int* list = m.scratch;
+  const int n = collect_desc(p, m, c, 1, list);
+  const U4* aj = (const U4*)(m.anc + (int64_t)j * p.Ws);
+  for (int r0 = 0; r0 < n; r0 += g.rpp) {
+    const int r = r0 + sub;
+    if (r < n) {
+      U4* ad = (U4*)(m.anc + (int64_t)list[r] * p.Ws);
+      for (int ch = li; ch < g.chunks; ch += g.lpr) {
+        U4 v = or4(ad[ch], aj[ch]);
+        if (ch == (j >> 7)) v = with_bit(v, j & 127);
+        ad[ch] = v;
       }
-      cnt = Warp::sum(cnt);
-      if (l == 0) m.anc_cnt[d0 + b] = cnt;
     }
   }
   Warp::sync();
 }
 
-// after removing a parent of child c: recompute anc for {c} u desc(c) in a
-// topological order.  |anc(x)| < |anc(d)| whenever x is an ancestor of d, so
-// sorting by the OLD ancestor counts gives such an order.
+// after removing a parent of child c (par[c] already updated).  If the remaining parents
+// still reach everything c reached, nothing changes anywhere (the common case in a graph
+// with redundant paths).  Otherwise recompute c and its descendants in a topological
+// order: |anc(x)| < |anc(d)| whenever x is an ancestor of d, so a counting sort by the OLD
+// ancestor counts gives such an order.
 BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
-  const int l = Warp::lane(), W = p.W, P = p.P;
-  int n = 0;
-  for (int d0 = 0; d0 < P; d0 += Warp::NL) {
-    const int d = d0 + l;
-    const int flag = (d < P) && (d == c || test_bit(m.anc + (int64_t)d * W, c));
-    const uint32_t mask = Warp::ballot(flag);
-    if (flag) {
-      const int off = popc32(mask & ((1u << l) - 1u));
-      m.sortbuf[n + off] = ((unsigned long long)(uint32_t)m.anc_cnt[d] << 32) | (uint32_t)d;
-    }
-    n += popc32(mask);
-  }
-  int n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  for (int i = n + l; i < n2; i += Warp::NL) m.sortbuf[i] = ~0ull;
-  Warp::sync();
-  // bitonic sort, ascending
-  for (int k = 2; k <= n2; k <<= 1) {
-    for (int jj = k >> 1; jj > 0; jj >>= 1) {
-      for (int i = l; i < n2; i += Warp::NL) {
-        const int ixj = i ^ jj;
-        if (ixj > i) {
-          const unsigned long long a = m.sortbuf[i], b = m.sortbuf[ixj];
-          const bool up = ((i & k) == 0);
-          if ((a > b) == up) { m.sortbuf[i] = b; m.sortbuf[ixj] = a; }
-        }
+  const RowGeom g = row_geom(p);
+  const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr, P = p.P;
+  {
+    const U4* ac = (const U4*)(m.anc + (int64_t)c * p.Ws);
+    const int* pc = m.par + (int64_t)c * p.max_par;
+    const int kc = m.npar[c];
+    int changed = 0;
+    for (int ch = l; ch < g.chunks; ch += Warp::NL) {
+      U4 v = {0u, 0u, 0u, 0u};
+      for (int e = 0; e < kc; e++) {
+        const int q = pc[e];
+        v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
+        if (ch == (q >> 7)) v = with_bit(v, q & 127);
       }
-      Warp::sync();
+      if (ne4(v, ac[ch])) changed = 1;
     }
+    if (Warp::ballot(changed) == 0u) return;
   }
-  for (int idx = 0; idx < n; idx++) {
-    const int d = (int)(uint32_t)(m.sortbuf[idx] & 0xffffffffull);
-    uint32_t* ad = m.anc + (int64_t)d * W;
-    const int* pd = m.par + (int64_t)d * p.max_par;
-    const int kd = m.npar[d];
+  const int st = scratch_stride(P);
+  int* list = m.scratch;
+  int* key = m.scratch + st;
+  int* hist = m.scratch + 2 * st;
+  int* order = m.scratch + 3 * st;
+  const int n = collect_desc(p, m, c, 0, list);  // proper descendants, old ancestor sets
+  for (int r0 = 0; r0 < n; r0 += g.rpp) {
+    const int r = r0 + sub;
     int cnt = 0;
-    for (int w = l; w < W; w += Warp::NL) {
-      uint32_t v = 0;
-      for (int e = 0; e < kd; e++) {
-        const int q = pd[e];
-        v |= m.anc[(int64_t)q * W + w];
-        if (w == (q >> 5)) v |= 1u << (q & 31);
-      }
-      ad[w] = v;
-      cnt += popc32(v);
+    if (r < n) {
+      const U4* ad = (const U4*)(m.anc + (int64_t)list[r] * p.Ws);
+      for (int ch = li; ch < g.chunks; ch += g.lpr) cnt += popc4(ad[ch]);
     }
-    cnt = Warp::sum(cnt);
-    if (l == 0) m.anc_cnt[d] = cnt;
+    cnt = group_sum(cnt, g.lpr);
+    if (r < n && li == 0) key[r] = cnt;
+  }
+  for (int i = l; i <= P; i += Warp::NL) hist[i] = 0;
+  Warp::sync();
+  for (int i = l; i < n; i += Warp::NL) atomic_fetch_inc(&hist[key[i]]);
+  Warp::sync();
+  {
+    const int per = (P + 1 + Warp::NL - 1) / Warp::NL;
+    const int lo = l * per;
+    int hi = lo + per;
+    if (hi > P + 1) hi = P + 1;
+    int local = 0;
+    for (int i = lo; i < hi; i++) local += hist[i];
+    int run = Warp::incl_scan(local) - local;
+    for (int i = lo; i < hi; i++) { const int t = hist[i]; hist[i] = run; run += t; }
+  }
+  Warp::sync();
+  for (int i = l; i < n; i += Warp::NL) order[atomic_fetch_inc(&hist[key[i]])] = list[i];
+  Warp::sync();
+  recompute_row(p, m, c, g.chunks);
+  Warp::sync();
+  for (int idx = 0; idx < n; idx++) {
+    recompute_row(p, m, order[idx], g.chunks);
     Warp::sync();
   }
 }
 
 // full build (chain start from a non-empty graph): Jacobi sweeps to the fixpoint
 BN_HD void anc_build_all(const ChainParams& p, ChainMem& m) {
-  const int l = Warp::lane(), W = p.W, P = p.P;
-  for (int64_t i = l; i < (int64_t)P * W; i += Warp::NL) m.anc[i] = 0u;
+  const RowGeom g = row_geom(p);
+  const int l = Warp::lane(), P = p.P;
+  for (int64_t i = l; i < (int64_t)P * p.Ws; i += Warp::NL) m.anc[i] = 0u;
   Warp::sync();
   for (int round = 0; round <= P; round++) {
     int changed = 0;
     for (int d = 0; d < P; d++) {
       const int kd = m.npar[d];
       if (kd == 0) continue;
-      uint32_t* ad = m.anc + (int64_t)d * W;
+      U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
       const int* pd = m.par + (int64_t)d * p.max_par;
-      for (int w = l; w < W; w += Warp::NL) {
-        uint32_t v = 0;
+      for (int ch = l; ch < g.chunks; ch += Warp::NL) {
+        U4 v = {0u, 0u, 0u, 0u};
         for (int e = 0; e < kd; e++) {
           const int q = pd[e];
-          v |= m.anc[(int64_t)q * W + w];
-          if (w == (q >> 5)) v |= 1u << (q & 31);
+          v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
+          if (ch == (q >> 7)) v = with_bit(v, q & 127);
         }
-        if (v != ad[w]) { ad[w] = v; changed = 1; }
+        if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
       }
       Warp::sync();
     }
     if (Warp::ballot(changed) == 0u) break;
-  }
-  for (int d = 0; d < P; d++) {
-    int cnt = 0;
-    for (int w = l; w < W; w += Warp::NL) cnt += popc32(m.anc[(int64_t)d * W + w]);
-    cnt = Warp::sum(cnt);
-    if (l == 0) m.anc_cnt[d] = cnt;
   }
   Warp::sync();
 }
@@ -270,18 +341,22 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   Warp::sync();
   if (s.te_true > 0) anc_build_all(p, m);
   else {
-    for (int64_t i = l; i < (int64_t)P * p.W; i += Warp::NL) m.anc[i] = 0u;
-    for (int i = l; i < P; i += Warp::NL) m.anc_cnt[i] = 0;
+    for (int64_t i = l; i < (int64_t)P * p.Ws; i += Warp::NL) m.anc[i] = 0u;
   }
   // base scores
   s.n_nonpd = 0;
-  {
-    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
-    int S[KMAX];
-    for (int c = l; c < P; c += Warp::NL) {
-      const int k = m.npar[c];
+  for (int c = l; c < P; c += Warp::NL) {
+    const int k = m.npar[c];
+    int npd = 0;
+    if constexpr (KMAX <= 8) {
+      int S[KMAX];
+#pragma unroll
+      for (int e = 0; e < KMAX; e++) S[e] = (e < k) ? m.par[(int64_t)c * MP + e] : c;
+      m.base[c] = score_set_small<KMAX>(p.C, p.ldc, c, S, k, p.n_samples, &npd);
+    } else {
+      double L[KMAX * (KMAX + 1) / 2], z[KMAX];
+      int S[KMAX];
       for (int e = 0; e < k; e++) S[e] = m.par[(int64_t)c * MP + e];
-      int npd = 0;
       m.base[c] = score_set(p.C, p.ldc, c, S, k, p.n_samples, L, z, &npd);
     }
   }
@@ -312,9 +387,7 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
                   const RngStream& rng, WindowSlots& ws, int want, int* overflow) {
   const int P = p.P, MP = p.max_par;
   int64_t pos = s.read_pos;
-  int valid = s.valid, te_m = s.te_m, fp_m = s.fp_m, fn_m = s.fn_m;
-  const int fp_true = s.te_true - s.agree_true;
-  const int fn_true = p.n_sim_edges - s.agree_true;
+  int valid = s.valid, te_m = s.te_m;
   const int64_t hi = rng.gen_hi;
   int n = 0;
   *overflow = 0;
@@ -347,9 +420,9 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
         if (ok) break;
       }
       type = 1;
-      te_m = s.te_true; fp_m = fp_true; fn_m = fn_true;  // OldLogPrior = LogPrior(), :302
+      te_m = s.te_true;  // OldLogPrior = LogPrior(), :302
       // CheckValidity -> pathExists (src/network.h:366-432): is c an ancestor of j?
-      if (!ovf) valid = !(j == c || test_bit(m.anc + (int64_t)j * p.W, c));
+      if (!ovf) valid = !(j == c || test_bit(m.anc + (int64_t)j * p.Ws, c));
     } else {
       // propose_deletion, src/network.h:308-328
       BN_U(u);  // drawn and discarded (:309)
@@ -362,23 +435,22 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
         j = m.par[(int64_t)c * MP + e];
       }
       type = 2;
-      te_m = s.te_true; fp_m = fp_true; fn_m = fn_true;  // :323
+      te_m = s.te_true;  // :323
       // `valid` keeps the previous iteration's value (src/bayesnet_mcmc.cpp:50-52)
     }
     double ua = 0.0;
     if (valid && !ovf) {
-      // checker(): NewLogPrior = LogPrior() on the proposed graph, src/network.h:333
-      const int ag = p.sim_edge[(int64_t)j + (int64_t)c * P] ? 1 : 0;
-      const int te_new = s.te_true + (type == 1 ? 1 : -1);
-      const int ag_new = s.agree_true + (type == 1 ? ag : -ag);
-      te_m = te_new; fp_m = te_new - ag_new; fn_m = p.n_sim_edges - ag_new;
+      // checker(): NewLogPrior = LogPrior() on the proposed graph (src/network.h:333) leaves
+      // TotalEdges at the proposed count; FP/FN need the prior adjacency and do not steer
+      // the draw order, so phase B fills them in (one lane per slot)
+      te_m = s.te_true + (type == 1 ? 1 : -1);
       BN_U(ua);  // acceptance uniform, :335
     }
     if (ovf) { *overflow = (n == 0); break; }
     if (Warp::lane() == 0) {
       ws.child[n] = c; ws.parent[n] = j; ws.pos[n] = e;
       ws.type[n] = (signed char)type; ws.valid[n] = (signed char)valid;
-      ws.te_m[n] = te_m; ws.fp_m[n] = fp_m; ws.fn_m[n] = fn_m;
+      ws.te_m[n] = te_m;
       ws.pos_after[n] = pos; ws.u_acc[n] = ua;
     }
     n++;
@@ -394,27 +466,57 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
 template <int KMAX>
 BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
                     WindowSlots& ws, int i) {
-  if (!ws.valid[i]) { ws.accept[i] = 0; ws.nonpd[i] = 0; return; }
   const int c = ws.child[i], j = ws.parent[i], MP = p.max_par;
+  const int fp_true = s.te_true - s.agree_true, fn_true = p.n_sim_edges - s.agree_true;
+  if (!ws.valid[i]) {
+    // invalid: only OldLogPrior ran, the members describe the current graph
+    ws.fp_m[i] = fp_true; ws.fn_m[i] = fn_true;
+    ws.accept[i] = 0; ws.nonpd[i] = 0; ws.kk[i] = 0;
+    return;
+  }
+  {
+    const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
+    const int ag_new = s.agree_true + (ws.type[i] == 1 ? ag : -ag);
+    ws.fp_m[i] = ws.te_m[i] - ag_new;
+    ws.fn_m[i] = p.n_sim_edges - ag_new;
+  }
   const int* pc = m.par + (int64_t)c * MP;
   const int k = m.npar[c];
-  double L[KMAX * (KMAX + 1) / 2], z[KMAX];
-  int S[KMAX];
   int kk = 0;
-  if (ws.type[i] == 1) {
-    for (int e = 0; e < k; e++) S[kk++] = pc[e];
-    S[kk++] = j;  // push_back, src/network.h:303
-  } else {
-    const int del = ws.pos[i];
-    for (int e = 0; e < k; e++) if (e != del) S[kk++] = pc[e];  // erase keeps the order, :325
-  }
   int npd = 0;
-  const double nw = score_set(p.C, p.ldc, c, S, kk, p.n_samples, L, z, &npd);
+  double nw;
+  if constexpr (KMAX <= 8) {
+    int S[KMAX];
+    if (ws.type[i] == 1) {
+      kk = k + 1;  // push_back, src/network.h:303
+#pragma unroll
+      for (int e = 0; e < KMAX; e++) S[e] = (e < k) ? pc[e] : j;
+    } else {
+      const int del = ws.pos[i];
+      kk = k - 1;  // erase keeps the order, :325
+#pragma unroll
+      for (int e = 0; e < KMAX; e++) {
+        const int src = e + (e >= del ? 1 : 0);
+        S[e] = (src < k) ? pc[src] : c;
+      }
+    }
+    nw = score_set_small<KMAX>(p.C, p.ldc, c, S, kk, p.n_samples, &npd);
+  } else {
+    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
+    int S[KMAX];
+    if (ws.type[i] == 1) {
+      for (int e = 0; e < k; e++) S[kk++] = pc[e];
+      S[kk++] = j;
+    } else {
+      const int del = ws.pos[i];
+      for (int e = 0; e < k; e++) if (e != del) S[kk++] = pc[e];
+    }
+    nw = score_set(p.C, p.ldc, c, S, kk, p.n_samples, L, z, &npd);
+  }
   ws.new_score[i] = nw;
   ws.kk[i] = kk;
   ws.nonpd[i] = (signed char)npd;
   // HR = exp(NewLogLike - OldLogLike + NewLogPrior - OldLogPrior), src/network.h:334
-  const int fp_true = s.te_true - s.agree_true, fn_true = p.n_sim_edges - s.agree_true;
   const double old_prior = prior_value(p.phi, p.omega, fp_true + fn_true, s.te_true);
   const double new_prior = prior_value(p.phi, p.omega, ws.fp_m[i] + ws.fn_m[i], ws.te_m[i]);
   const double arg = sub_rn(add_rn(sub_rn(nw, m.base[c]), new_prior), old_prior);

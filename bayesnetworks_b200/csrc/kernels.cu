@@ -14,21 +14,23 @@ namespace bn {
 // ---------------------------------------------------------------------------
 template <int KMAX>
 __global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
-                                                   ChainResult* __restrict__ results) {
+                                                   ChainSmemPlan sm, ChainResult* __restrict__ results) {
   __shared__ double ubuf[RNG_CAP];
   __shared__ WindowSlots ws;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int ch = blockIdx.x;
   const int64_t P = p.P, MP = p.max_par, W = p.W;
 
   ChainMem m;
-  m.par = w.par + ch * P * MP;
-  m.npar = w.npar + ch * P;
+  int* g_par = w.par + ch * P * MP;
+  int* g_npar = w.npar + ch * P;
+  m.par = sm.off_par >= 0 ? (int*)(dyn_smem + sm.off_par) : g_par;
+  m.npar = sm.off_npar >= 0 ? (int*)(dyn_smem + sm.off_npar) : g_npar;
   m.born = w.born + ch * P * MP;
-  m.base = w.base + ch * P;
-  m.anc = w.anc + ch * P * W;
-  m.anc_cnt = w.anc_cnt + ch * P;
-  m.haspar = w.haspar + ch * W;
-  m.sortbuf = w.sortbuf + (int64_t)ch * w.sort_n;
+  m.base = sm.off_base >= 0 ? (double*)(dyn_smem + sm.off_base) : w.base + ch * P;
+  m.anc = sm.off_anc >= 0 ? (uint32_t*)(dyn_smem + sm.off_anc) : w.anc + ch * P * (int64_t)p.Ws;
+  m.haspar = sm.off_haspar >= 0 ? (uint32_t*)(dyn_smem + sm.off_haspar) : w.haspar + ch * W;
+  m.scratch = sm.off_scratch >= 0 ? (int*)(dyn_smem + sm.off_scratch) : w.scratch + (int64_t)ch * w.scratch_n;
   const int64_t cap = p.trace_capacity;
   m.t_iter = w.t_iter + ch * cap; m.t_changed = w.t_changed + ch * cap;
   m.t_movetype = w.t_movetype + ch * cap; m.t_gll = w.t_gll + ch * cap;
@@ -47,8 +49,20 @@ __global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace
 
   ChainParams pp = p;
   if (!m.moves) pp.moves_capacity = 0;
+  if (sm.off_types >= 0) {
+    uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);
+    for (int i = threadIdx.x; i < p.P; i += 32) t[i] = p.node_type[i];
+    __syncwarp();
+    pp.node_type = t;
+  }
   ChainScalars s;
   run_chain<KMAX>(pp, m, s, rng, ws);
+
+  // final graph back to global memory when it lived in shared memory
+  if (m.par != g_par)
+    for (int64_t i = threadIdx.x; i < P * MP; i += 32) g_par[i] = m.par[i];
+  if (m.npar != g_npar)
+    for (int64_t i = threadIdx.x; i < P; i += 32) g_npar[i] = m.npar[i];
 
   if (threadIdx.x == 0) {
     ChainResult& r = results[ch];
@@ -65,13 +79,59 @@ __global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace
   }
 }
 
-const char* launch_chains(const ChainParams& p, const ChainWorkspace& w, const ChainRngArgs& ra,
-                          ChainResult* d_results, int n_chains, cudaStream_t stream) {
-  if (p.max_par <= 8) chain_kernel<8><<<n_chains, 32, 0, stream>>>(p, w, ra, d_results);
-  else if (p.max_par <= 16) chain_kernel<16><<<n_chains, 32, 0, stream>>>(p, w, ra, d_results);
-  else if (p.max_par <= 64) chain_kernel<64><<<n_chains, 32, 0, stream>>>(p, w, ra, d_results);
-  else return "max_par > 64 is not supported";
+// Greedy placement of the per-chain arrays into the CTA's dynamic shared memory, hottest
+// and smallest first; the ancestor bitsets get an odd row stride so that the column scan
+// of anc_after_add/delete (one row per lane) is bank-conflict free.
+static ChainSmemPlan plan_chain_smem(ChainParams& p, int scratch_n, int budget) {
+  ChainSmemPlan sm;
+  int used = 0;
+  auto place = [&](int64_t bytes) -> int {
+    const int64_t b = (bytes + 15) / 16 * 16;
+    if (used + b > budget) return -1;
+    const int off = used;
+    used += (int)b;
+    return off;
+  };
+  const int64_t P = p.P, MP = p.max_par, W = p.W;
+  sm.off_types = place(P);
+  sm.off_npar = place(P * 4);
+  sm.off_base = place(P * 8);
+  sm.off_haspar = place(W * 4);
+  sm.off_par = place(P * MP * 4);
+  sm.off_scratch = place((int64_t)scratch_n * 4);
+  // in shared memory, keep the row stride off a multiple of 32 words so that the column
+  // scan (one row per lane, same word) spreads over the banks
+  int64_t Ws = anc_stride((int)W);
+  if (Ws % 32 == 0) Ws += 4;
+  sm.off_anc = place(P * Ws * 4);
+  p.Ws = sm.off_anc >= 0 ? (int)Ws : anc_stride((int)W);
+  sm.total_bytes = used;
+  return sm;
+}
+
+template <int KMAX>
+static const char* launch_chains_t(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
+                                   ChainResult* d_results, int n_chains, cudaStream_t stream) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, chain_kernel<KMAX>) != cudaSuccess) return "cudaFuncGetAttributes failed";
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int budget = max_optin - (int)fa.sharedSizeBytes - 1024;
+  ChainSmemPlan sm = plan_chain_smem(p, w.scratch_n, budget > 0 ? budget : 0);
+  if (cudaFuncSetAttribute(chain_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           sm.total_bytes) != cudaSuccess)
+    return "cudaFuncSetAttribute(chain_kernel) failed";
+  chain_kernel<KMAX><<<n_chains, 32, sm.total_bytes, stream>>>(p, w, ra, sm, d_results);
   return nullptr;
+}
+
+const char* launch_chains(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
+                          ChainResult* d_results, int n_chains, cudaStream_t stream) {
+  if (p.max_par <= 8) return launch_chains_t<8>(p, w, ra, d_results, n_chains, stream);
+  if (p.max_par <= 16) return launch_chains_t<16>(p, w, ra, d_results, n_chains, stream);
+  if (p.max_par <= 64) return launch_chains_t<64>(p, w, ra, d_results, n_chains, stream);
+  return "max_par > 64 is not supported";
 }
 
 // ---------------------------------------------------------------------------

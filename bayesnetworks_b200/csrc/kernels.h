@@ -9,12 +9,23 @@ namespace bn {
 
 struct ChainWorkspace {  // arrays over all chains of a run (device memory)
   int* par; int* npar; int* born; double* base;
-  uint32_t* anc; int* anc_cnt; uint32_t* haspar;
-  unsigned long long* sortbuf; int sort_n;
+  uint32_t* anc; uint32_t* haspar;   // anc rows are anc_stride(W) words apart in global memory
+  int* scratch; int scratch_n;        // 4 * scratch_stride(P) ints per chain
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
   int* t_add; int* t_del; int* t_fn; int* t_fp;
   int* moves; int* edge_freq;
 };
+
+// Which per-chain arrays live in dynamic shared memory (byte offset, -1 = global memory).
+// One chain = one CTA, so the hot state (parent lists, scores, ancestor bitsets) sits
+// ~30 cycles away instead of an L2 round trip; arrays that do not fit stay in global.
+struct ChainSmemPlan {
+  int off_types, off_npar, off_base, off_haspar, off_par, off_scratch, off_anc;
+  int total_bytes;
+};
+
+// row stride (words) of the ancestor bitsets: a multiple of 4 (128-bit chunks)
+inline int anc_stride(int W) { return (W + 3) / 4 * 4; }
 
 struct ChainRngArgs {
   int kind;
@@ -40,7 +51,7 @@ struct SweepParams {
   double* out_base; double* out_score; double* out_log_hr;
 };
 
-const char* launch_chains(const ChainParams& p, const ChainWorkspace& w, const ChainRngArgs& ra,
+const char* launch_chains(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
                           ChainResult* d_results, int n_chains, cudaStream_t stream);
 const char* launch_score_nodes(const double* C, int64_t ldc, int n_samples, int max_par, int n_items,
                                const int* d_child, const int* d_parents, const int* d_npar, double* d_out,

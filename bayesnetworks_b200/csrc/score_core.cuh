@@ -59,4 +59,56 @@ BN_HD double score_set(const double* __restrict__ C, int64_t ldc, int c,
   return -((double)n_samples / 2.0) * log(resid2 / syy);
 }
 
+// Register-resident variant for small parent limits (K <= 8): every index is a
+// compile-time constant after unrolling, so the factor lives in registers, the gathers
+// issue back to back (one L2 round trip instead of one per row) and the divisions
+// become multiplications by the reciprocal pivot.
+template <int K>
+BN_HD double score_set_small(const double* __restrict__ C, int64_t ldc, int c, const int (&S)[K], int k,
+                             int n_samples, int* nonpd) {
+  double L[K * (K + 1) / 2], z[K], rinv[K];
+  const double Ccc = ld_shared_ro(C + (int64_t)c * ldc + c);
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    const bool on = i < k;
+    const double* row = C + (int64_t)(on ? S[i] : c) * ldc;
+#pragma unroll
+    for (int m = 0; m <= i; m++) L[i * (i + 1) / 2 + m] = on ? ld_shared_ro(row + S[m]) : 0.0;
+    z[i] = on ? ld_shared_ro(row + c) : 0.0;
+  }
+  double rss = Ccc;
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    if (i < k) {
+#pragma unroll
+      for (int m = 0; m < i; m++) {
+        double acc = L[i * (i + 1) / 2 + m];
+#pragma unroll
+        for (int t = 0; t < m; t++) acc -= L[i * (i + 1) / 2 + t] * L[m * (m + 1) / 2 + t];
+        L[i * (i + 1) / 2 + m] = acc * rinv[m];
+      }
+      double d = L[i * (i + 1) / 2 + i];
+#pragma unroll
+      for (int t = 0; t < i; t++) d -= L[i * (i + 1) / 2 + t] * L[i * (i + 1) / 2 + t];
+      if (!(d > 0.0)) { bad = true; d = 1.0; }
+      const double r = 1.0 / sqrt(d);
+      rinv[i] = r;
+      double acc = z[i];
+#pragma unroll
+      for (int t = 0; t < i; t++) acc -= L[i * (i + 1) / 2 + t] * z[t];
+      acc *= r;
+      z[i] = acc;
+      rss -= acc * acc;
+    }
+  }
+  if (bad) {
+    if (nonpd) *nonpd = 1;
+    return -INFINITY;
+  }
+  const double resid2 = rss / (double)(n_samples - k - 1);
+  const double syy = Ccc / (double)(n_samples - 1);
+  return -((double)n_samples / 2.0) * log(resid2 / syy);
+}
+
 }  // namespace bn

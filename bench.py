@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- edge proposals scored/sec and MCMC iters/sec of the structure-MCMC hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): synthetic
+linear-Gaussian DAG, 1,000 nodes x 100,000 samples, MaxPar 8, 64 chains per GPU (weak
+scaling: chains are independent and sharded by global index), 100,000 iterations per chain,
+a trace row every 100 iterations.
+
+A "step" is one whole job on that input: sufficient statistics (Gram) + all chains.
+  value : job throughput with X already resident in HBM (bn_create_from_device + bn_run),
+          timed with CUDA events on the launching stream, max over ranks.
+  e2e   : the same job through the host-pointer API (bn_create + bn_run): X starts in pinned
+          host memory, H2D inside the timed region, traces copied back to the host.
+One proposal scored = one iteration that reached checker() (src/network.h:330-336), i.e. one
+evaluation of a proposed parent set -- the definition under which the reference's
+iterations/s equals its proposals/s.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified
+sources compiled by oracle/Makefile; else the oracle port) on all host cores, one chain per
+core, on a bounded row-subsample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "edge_proposals_scored_per_sec"
+UNIT = "proposals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=1000)
+    ap.add_argument("--samples", type=int, default=100000)
+    ap.add_argument("--max-par", type=int, default=8)
+    ap.add_argument("--chains-per-gpu", type=int, default=64)
+    ap.add_argument("--iters", type=int, default=100000)
+    ap.add_argument("--output", type=int, default=100)
+    ap.add_argument("--ref-rows", type=int, default=1000, help="row subsample of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the K1/K2 side measurements")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic Gaussian DAG {a.nodes} nodes x {a.samples} samples, MaxPar {a.max_par}, "
+            f"{a.chains_per_gpu} chains/GPU x {a.iters} iters, output every {a.output}")
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# reference arm (CPU)
+# ---------------------------------------------------------------------------
+def _ref_worker(job):
+    (use_ref, X, src, tgt, nt, max_par, n_iter, output, seeds) = job
+    from oracle.oracle import RNG_WH, Oracle, Ref
+    t0 = time.perf_counter()
+    if use_ref:
+        r = Ref().main_fun(X, src, tgt, nt, MaxPar=max_par, N=n_iter, output=output, rng_kind=RNG_WH, seeds=seeds)
+        rows = len(r.iter)
+    else:
+        r = Oracle().mcmc(X, src, tgt, nt, max_par=max_par, n_iter=n_iter, output=output, rng_kind=RNG_WH,
+                          seeds=seeds, log_moves=False)
+        rows = len(r.iter)
+    return time.perf_counter() - t0, rows
+
+
+def reference_sample(a, cores=None):
+    """One step of the reference arm: `cores` independent chains (one process each) on a row
+    subsample.  Returns (proposals/s, iters/s, seconds, description dict)."""
+    import multiprocessing as mp
+    from bayesnetworks_b200.synth import chain_seeds, make_dag, make_prior, simulate_numpy
+    from oracle.oracle import have_ref
+    cores = cores or os.cpu_count() or 1
+    dag = make_dag(a.nodes, seed=42)
+    g = make_prior(dag, max_par=a.max_par, seed=43)
+    rows = min(a.ref_rows, a.samples)
+    X = simulate_numpy(dag, rows, seed=42)
+    nt = g.node_type_codes()
+    use_ref = have_ref()
+    seeds = chain_seeds(cores)
+    jobs = [(use_ref, X, g.source, g.target, nt, a.max_par, a.iters, a.output, tuple(int(v) for v in seeds[c]))
+            for c in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    # every iteration of the reference that reaches checker() scores one proposal; invalid
+    # (cyclic) proposals are <0.2% of iterations, so iterations are counted as proposals here
+    total_iters = cores * a.iters
+    desc = {"kind": "reference" if use_ref else "port", "cores": cores,
+            "sample": (f"{cores} chains (one per core) x {a.iters} iters on {a.nodes} nodes x {rows} of "
+                       f"{a.samples} rows (row subsample; the reference's per-proposal cost grows with the "
+                       f"row count, so this overstates its full-size throughput), Gram/ctor included")}
+    return total_iters / wall, total_iters / wall, wall, desc
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, secs = [], []
+    desc = None
+    for i in range(a.warmup + a.steps):
+        v, _, wall, desc = reference_sample(a)
+        if i >= a.warmup:
+            vals.append(v); secs.append(wall)
+    value = float(np.mean(vals)) if vals else 0.0
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(secs)) if secs else None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(a), "l2": "n/a (CPU)"},
+            "iters_per_sec": value, "gpu_launches": 0,
+            "cpu_baseline": dict(desc, value=value, unit=UNIT),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm (GPU)
+# ---------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from bayesnetworks_b200 import Context, set_default_stream
+    from bayesnetworks_b200.dist import shard_chains
+    from bayesnetworks_b200.synth import chain_seeds, make_dag, make_prior, simulate_torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_chains_total = a.chains_per_gpu * world  # weak scaling: fixed work per GPU
+    first, count = shard_chains(n_chains_total, world, rank)
+    seeds = chain_seeds(count, first_chain=first)
+
+    dag = make_dag(a.nodes, seed=42)
+    g = make_prior(dag, max_par=a.max_par, seed=43)
+    nt = g.node_type_codes()
+    X = simulate_torch(dag, a.samples, seed=42, device=dev)  # (P, N): column-major N x P
+    torch.cuda.synchronize()
+    x_bytes = X.numel() * 8
+    stream = torch.cuda.current_stream().cuda_stream
+    set_default_stream(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    state = {}
+
+    def step_resident():
+        with Context.from_device(X.data_ptr(), a.samples, a.samples, a.nodes, g.source, g.target, nt,
+                                 max_par=a.max_par, device=local_rank) as ctx:
+            res, ms = ctx.run(n_chains=count, n_iter=a.iters, output=a.output, rng="wh", seeds=seeds)
+            state.update(res=res, chain_ms=ms, gram_ms=ctx.gram_ms, launches=ctx.launch_count)
+
+    Xh = torch.empty((a.nodes, a.samples), dtype=torch.float64, pin_memory=True)
+    Xh.copy_(X)
+    Xh_np = Xh.numpy().T  # (N, P) Fortran-ordered view of the pinned buffer
+
+    def step_e2e():
+        with Context.from_data(Xh_np, g.source, g.target, nt, max_par=a.max_par, device=local_rank) as ctx:
+            res, ms = ctx.run(n_chains=count, n_iter=a.iters, output=a.output, rng="wh", seeds=seeds)
+            state.update(res_e2e=res)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_resident, a.steps, a.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = timed(step_e2e, a.steps, max(1, a.warmup // 3))
+
+    # per-step work (identical every step: same seeds)
+    res = state["res"]
+    local = torch.tensor([sum(r.valid_iters for r in res), count * a.iters, sum(r.alg_bytes for r in res),
+                          sum(len(r.trace["iter"]) for r in res)], dtype=torch.float64, device=dev)
+    kern = torch.tensor([state["chain_ms"], state["gram_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    proposals, iters, alg_bytes, rows = [float(v) for v in local.tolist()]
+    chain_ms, gram_ms = [float(v) for v in kern.tolist()]
+    ms_per_step = total_ms / a.steps
+    e2e_ms_per_step = e2e_ms / a.steps
+    # parity guard inside the bench: the e2e path must give the same trajectories
+    same = all(np.array_equal(r1.trace["ChangedNode"], r2.trace["ChangedNode"])
+               for r1, r2 in zip(state["res"], state["res_e2e"]))
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    # dominant kernel of the step = the persistent chain kernel (one launch per step per GPU)
+    per_gpu_bytes = alg_bytes / world
+    achieved = per_gpu_bytes / (chain_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "chain_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": chain_ms, "share_of_step": chain_ms / ms_per_step,
+                "note": "latency-bound sequential chains: algorithmic gather bytes = sum over scored "
+                        "proposals of 8*(k'+1)(k'+2)/2+8 (SURVEY.md 8d); the Gram (8 MB) is L2 resident"}
+
+    line = {"metric": METRIC, "value": proposals / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "chains_total": n_chains_total,
+                       "l2": "inputs larger than L2 (X = %.0f MB per GPU, re-read every step)" % (x_bytes / 1e6),
+                       "parallelism": f"chains sharded over {world} GPU(s), no data-path collective"},
+            "iters_per_sec": iters / (ms_per_step * 1e-3),
+            "clocks": clocks,
+            "e2e": {"value": proposals / (e2e_ms_per_step * 1e-3), "unit": UNIT,
+                    "iters_per_sec": iters / (e2e_ms_per_step * 1e-3), "ms_per_step": e2e_ms_per_step,
+                    "h2d_bytes_per_step": int(x_bytes + 4 * (2 * len(g.source) + a.nodes) + 12 * count),
+                    "d2h_bytes_per_step": int(count * max(1, (a.iters + a.output - 1) // a.output) * 36 + 64 * count),
+                    "same_trajectories_as_resident_path": bool(same)},
+            "gpu_launches": int(state["launches"]) * a.steps,
+            "roofline": roofline,
+            "step_breakdown_ms": {"gram_build": gram_ms, "chain_kernel": chain_ms},
+            "trace_rows_per_step": rows}
+
+    if not a.no_kernels:
+        line["kernels"] = side_kernels(a, X, g, nt, state["res"], local_rank, hbm_peak)
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            v, _, wall, desc = reference_sample(a)
+            line["cpu_baseline"] = dict(desc, value=v, unit=UNIT, seconds=wall)
+        except Exception as exc:  # the baseline is a reported number, never a dependency
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def side_kernels(a, X, g, nt, res, local_rank, hbm_peak):
+    """K1 (Gram, FP64 tensor pipe) and K2 (all-proposal sweep) timed alone, plus the in-run
+    cuBLAS DGEMM figure that stands in for the FP64 peak (MEASURED_PEAKS.json has none)."""
+    import torch
+    from bayesnetworks_b200 import Context
+    out = {}
+    P, N = a.nodes, a.samples
+    # cuBLAS DGEMM (library call: denominator only, not on the product path)
+    n = 8192
+    A = torch.randn((n, n), dtype=torch.float64, device=X.device)
+    B = torch.randn((n, n), dtype=torch.float64, device=X.device)
+    for _ in range(2):
+        torch.matmul(A, B)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(A, B); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    dgemm_tf = 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    del A, B
+    gram_ms = []
+    with Context.from_device(X.data_ptr(), N, N, P, g.source, g.target, nt, max_par=a.max_par,
+                             device=local_rank) as ctx:
+        gram_ms.append(ctx.gram_ms)
+        # K2: sweep over the chains' final graphs
+        G = len(res)
+        par = np.stack([r.final_parents for r in res]).astype(np.int32)
+        npar = np.stack([r.final_npar for r in res]).astype(np.int32)
+        d_par = torch.from_numpy(par).to(X.device)
+        d_np = torch.from_numpy(npar).to(X.device)
+        d_base = torch.empty((G, P), dtype=torch.float64, device=X.device)
+        d_score = torch.empty((G, P, P), dtype=torch.float64, device=X.device)
+        d_hr = torch.empty((G, P, P), dtype=torch.float64, device=X.device)
+        ms = [ctx.score_all_proposals_device(G, d_par.data_ptr(), d_np.data_ptr(), d_base.data_ptr(),
+                                             d_score.data_ptr(), d_hr.data_ptr()) for _ in range(6)][1:]
+        sweep_ms = float(np.mean(ms))
+        score = d_score.cpu().numpy()
+        scored = int(np.isfinite(score).sum())
+        kk = npar.astype(np.int64)
+        # algorithmic bytes: adds score k+1 parents, deletes k-1 (8*(k'+1)(k'+2)/2 + 8 each)
+        is_par = np.zeros((G, P, P), bool)
+        for gi in range(G):
+            for c in range(P):
+                is_par[gi, c, par[gi, c, :npar[gi, c]]] = True
+        kprime = np.where(is_par, kk[:, :, None] - 1, kk[:, :, None] + 1)
+        alg = float(np.where(np.isfinite(score), 4 * (kprime + 1) * (kprime + 2) + 8, 0).sum())
+        out["sweep"] = {"ms": sweep_ms, "graphs": G, "proposals_scored": scored,
+                        "proposals_per_sec": scored / (sweep_ms * 1e-3),
+                        "roofline": {"bound": "hbm", "achieved": alg / (sweep_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": alg / (sweep_ms * 1e-3) / 1e9 / hbm_peak,
+                                     "min_traffic_GBps": (scored * 8.0 * 2 + G * P * 8.0) / (sweep_ms * 1e-3) / 1e9,
+                                     "note": "achieved = algorithmic per-proposal gather bytes (SURVEY.md 8d); the "
+                                             "kernel shares one factorisation per child, so its real traffic is the "
+                                             "two output tables (min_traffic_GBps)"}}
+    for _ in range(3):
+        with Context.from_device(X.data_ptr(), N, N, P, g.source, g.target, nt, max_par=a.max_par,
+                                 device=local_rank) as ctx:
+            gram_ms.append(ctx.gram_ms)
+    gm = float(np.min(gram_ms[1:]))
+    tiles = (P + 127) // 128
+    executed = tiles * (tiles + 1) / 2 * 128 * 128 * 2.0 * N
+    out["gram"] = {"ms": gm, "tflops_full_count": 2.0 * N * P * P / (gm * 1e-3) / 1e12,
+                   "tflops_executed": executed / (gm * 1e-3) / 1e12, "dgemm_cublas_tflops": dgemm_tf,
+                   "roofline": {"bound": "tensor", "achieved": executed / (gm * 1e-3) / 1e12, "peak": dgemm_tf,
+                                "unit": "TFLOP/s", "frac": executed / (gm * 1e-3) / 1e12 / dgemm_tf,
+                                "note": "FP64 DMMA; peak = cuBLAS DGEMM 8192^3 measured in this run (no FP64 figure "
+                                        "in MEASURED_PEAKS.json); ms covers means+centring+DMMA+reduce"}}
+    return out
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -83,9 +83,18 @@ int bn_create_from_stats(int n_samples, int n_nodes, const double* mean,
 
 void bn_destroy(bn_ctx* ctx);
 
+/* Scratch device buffers are pooled per device between calls (cudaMalloc/cudaFree cost more
+ * than the kernels); this returns the idle ones to the driver.  BN_B200_POOL=0 disables. */
+int bn_trim_pool(void);
+
 /* Launch all subsequent work of this context on the given cudaStream_t
  * (passed as void*); NULL restores the context's own stream. */
 int bn_set_stream(bn_ctx* ctx, void* cuda_stream);
+
+/* Stream that contexts created afterwards BY THIS THREAD start on (so that the
+ * Gram build of bn_create* can be bracketed by the caller's CUDA events); NULL =
+ * each context creates its own non-blocking stream (the default). */
+int bn_set_default_stream(void* cuda_stream);
 
 /* Read back the sufficient statistics.  Any pointer may be NULL.
  *   sum_x[p]            = sum_n X(n,p)                       (src/network.h:129)

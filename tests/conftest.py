@@ -49,7 +49,7 @@ def emu_lib():
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         os.makedirs(out_dir, exist_ok=True)
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared",
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-w",
                                "-x", "c++", f"-I{csrc}", "-o", so, src])
     lib = ctypes.CDLL(so)
     lib.emu_score_set.restype = ctypes.c_double

@@ -22,24 +22,24 @@ extern "C" int emu_run_chain(
     int* t_fn, int* t_fp, int moves_capacity, int* moves, int* edge_freq,
     int* final_par, int* final_npar, long* out_counters /*[12]*/) {
   ChainParams p;
-  p.P = P; p.max_par = max_par; p.W = (P + 31) / 32; p.n_samples = n_samples;
+  p.P = P; p.max_par = max_par; p.W = (P + 31) / 32; p.Ws = (p.W + 3) / 4 * 4; p.n_samples = n_samples;
   p.C = C; p.ldc = P; p.node_type = node_type; p.sim_edge = sim_edge;
   p.n_sim_edges = n_sim_edges; p.phi = phi; p.omega = omega;
   p.initial_network = initial_network; p.drop = drop; p.n_iter = n_iter;
   p.output_every = output_every; p.trace_capacity = capacity; p.moves_capacity = moves_capacity;
   p.prior_par = prior_par; p.prior_npar = prior_npar;
 
-  std::vector<int> par((size_t)P * max_par), npar(P), born((size_t)P * max_par), anc_cnt(P);
+  std::vector<int> par((size_t)P * max_par), npar(P), born((size_t)P * max_par);
+  std::vector<int> scratch((size_t)4 * scratch_stride(P));
   std::vector<double> base(P);
-  std::vector<uint32_t> anc((size_t)P * p.W), haspar(p.W);
-  size_t n2 = 1; while (n2 < (size_t)P) n2 <<= 1;
-  std::vector<unsigned long long> sortbuf(n2);
+  std::vector<uint32_t> anc_store((size_t)P * p.Ws + 4), haspar(p.W);
+  uint32_t* anc = (uint32_t*)(((uintptr_t)anc_store.data() + 15) & ~(uintptr_t)15);
   std::vector<uint32_t> mt(624);
   if (mt_state) memcpy(mt.data(), mt_state, 624 * 4);
   ChainMem m;
   m.par = par.data(); m.npar = npar.data(); m.born = born.data(); m.base = base.data();
-  m.anc = anc.data(); m.anc_cnt = anc_cnt.data(); m.haspar = haspar.data();
-  m.sortbuf = sortbuf.data();
+  m.anc = anc; m.haspar = haspar.data();
+  m.scratch = scratch.data();
   m.t_iter = t_iter; m.t_changed = t_changed; m.t_movetype = t_movetype; m.t_gll = t_gll;
   m.t_add = t_add; m.t_del = t_del; m.t_fn = t_fn; m.t_fp = t_fp;
   m.moves = moves; m.edge_freq = edge_freq;
