@@ -23,6 +23,7 @@
 #include <iostream>
 #include <initializer_list>
 #include <utility>
+#include <stdexcept>
 
 namespace Rcpp {
 
@@ -114,6 +115,9 @@ struct ShimErrStream {
   template <typename T> ShimErrStream& operator<<(const T&) { n_messages++; return *this; }
 };
 extern ShimErrStream Rcerr;
+
+// Rcpp::stop -> C++ exception (BEGIN_RCPP/END_RCPP turn it into an R error)
+inline void stop(const std::string& msg) { throw std::runtime_error(msg); }
 
 }  // namespace Rcpp
 

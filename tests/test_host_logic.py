@@ -262,6 +262,24 @@ def test_argument_validation_before_device():
     assert ei.value.status == _lib.BN_ERR_BAD_ARG
 
 
+def test_rcpp_glue_compiles_against_shim():
+    """The drop-in src/bayesnet_mcmc.cpp replacement keeps the reference's exported signature
+    and compiles against the stand-in Rcpp.h (R itself is not installed here)."""
+    import subprocess
+    glue = os.path.join(ROOT, "bayesnetworks_b200", "csrc", "rcpp_glue", "bayesnet_mcmc.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-w",
+                           f"-I{os.path.join(ROOT, 'oracle', 'ref_shim')}",
+                           f"-I{os.path.join(ROOT, 'include')}", glue])
+    text = open(glue).read()
+    for frag in ("DataFrame main_fun(NumericMatrix X,", "std::vector<int> graph_node_labels,",
+                 "int MaxPar = 50,", "const double phi = 1,", "const double omega = 6.9,",
+                 "const int InitialNetwork = 2,", "const int drop = 0,", "int N = 1000,",
+                 "int output = 10)"):
+        assert frag in text, frag
+    cols = re.findall(r'Named\("(\w+)"\)', text)
+    assert cols == ["iter", "ChangedNode", "movetype", "globalLL", "additions", "deletions", "FN", "FP"]
+
+
 def test_product_never_imports_oracle():
     """Nothing under bayesnetworks_b200/ imports, links or dlopens anything under oracle/."""
     pkg = os.path.join(ROOT, "bayesnetworks_b200")
