@@ -529,6 +529,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   CU_TRY(buf.alloc(&w.base, (size_t)(nc * P)));
   CU_TRY(buf.alloc(&w.anc, (size_t)(nc * P * anc_stride((int)W))));
   CU_TRY(buf.alloc(&w.haspar, (size_t)(nc * W)));
+  CU_TRY(buf.alloc(&w.hp_list, (size_t)(nc * P)));
   CU_TRY(buf.alloc(&w.scratch, (size_t)nc * w.scratch_n));
   const bool dev_out = a->device_outputs != 0;
   if (dev_out) {

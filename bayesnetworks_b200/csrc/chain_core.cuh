@@ -51,7 +51,8 @@ struct ChainMem {  // per-chain global memory
   int* born;           // [P][max_par] first counted iteration of the edge (tabulation)
   double* base;        // [P] score of each node under the current graph
   uint32_t* anc;       // [P][Ws] ancestor bitsets
-  uint32_t* haspar;    // [W] nodes with >= 1 parent
+  uint32_t* haspar;    // [W] nodes with >= 1 parent (bitset)
+  int* hp_list;        // [P] the same set as an ascending list (CurrOutputs, src/network.h:311-316)
   int* scratch;        // [4 * scratch_stride(P)] lists / keys / histogram for the ancestor updates
   // outputs
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
@@ -82,6 +83,9 @@ struct WindowSlots {  // shared memory on the device
   int64_t pos_after[WIN];
   double u_acc[WIN], new_score[WIN];
   signed char type[WIN], valid[WIN], do_check[WIN], accept[WIN], nonpd[WIN];
+  // lane-parallel draw replay: outcome of a slot that would start at stream position pos + lane
+  int t_c[WIN], t_j[WIN], t_e[WIN], t_consumed[WIN];
+  signed char t_type[WIN], t_cyc[WIN], t_ovf[WIN];
 };
 
 BN_HD bool test_bit(const uint32_t* row, int b) { return (row[b >> 5] >> (b & 31)) & 1u; }
@@ -92,30 +96,42 @@ BN_HD double prior_value(double phi, double omega, int dist, int total_edges) {
   return sub_rn(mul_rn(-phi, (double)dist), mul_rn(omega, (double)total_edges));
 }
 
-// index of the k-th (0-based) set bit of a W-word bitset, by the whole warp
-BN_HD int select_kth(const uint32_t* bits, int W, int k) {
-  const int l = Warp::lane();
-  int before = 0;
-  for (int w0 = 0; w0 < W; w0 += Warp::NL) {
-    const int w = w0 + l;
-    uint32_t word = (w < W) ? bits[w] : 0u;
-    const int cnt = popc32(word);
-    const int incl = Warp::incl_scan(cnt);
-    const int total = Warp::shfl(incl, Warp::NL - 1);
-    if (k < before + total) {
-      const uint32_t m = Warp::ballot(before + incl > k);
-      const int src = ffs32(m) - 1;
-      int r = k - before - (incl - cnt);
-      int res = -1;
-      if (l == src) {
-        for (int i = 0; i < r; i++) word &= word - 1;
-        res = w * 32 + ffs32(word) - 1;
-      }
-      return Warp::shfl(res, src);
-    }
-    before += total;
+// number of set bits of a bitset strictly below position c, by the whole warp
+BN_HD int rank_below(const uint32_t* bits, int c) {
+  const int l = Warp::lane(), cw = c >> 5;
+  int cnt = 0;
+  for (int w = l; w <= cw; w += Warp::NL) {
+    uint32_t word = bits[w];
+    if (w == cw) word &= (1u << (c & 31)) - 1u;
+    cnt += popc32(word);
   }
-  return -1;
+  return Warp::sum(cnt);
+}
+
+// keep hp_list (ascending nodes with >= 1 parent) in step with the haspar bitset
+BN_HD void hp_insert(ChainMem& m, int n_before, int c) {
+  const int l = Warp::lane();
+  const int idx = rank_below(m.haspar, c);
+  for (int hi = n_before; hi > idx; hi -= Warp::NL) {
+    const int i = hi - 1 - l;
+    const int v = (i >= idx) ? m.hp_list[i] : 0;
+    Warp::sync();
+    if (i >= idx) m.hp_list[i + 1] = v;
+    Warp::sync();
+  }
+  if (l == 0) m.hp_list[idx] = c;
+  Warp::sync();
+}
+BN_HD void hp_remove(ChainMem& m, int n_before, int c) {
+  const int l = Warp::lane();
+  const int idx = rank_below(m.haspar, c);
+  for (int lo = idx; lo < n_before - 1; lo += Warp::NL) {
+    const int i = lo + l;
+    const int v = (i < n_before - 1) ? m.hp_list[i + 1] : 0;
+    Warp::sync();
+    if (i < n_before - 1) m.hp_list[i] = v;
+    Warp::sync();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -327,7 +343,7 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
     int te = 0, ag = 0, nh = 0;
     for (int c = 0; c < P; c++) {
       const int k = m.npar[c];
-      if (k) { m.haspar[c >> 5] |= 1u << (c & 31); nh++; }
+      if (k) { m.haspar[c >> 5] |= 1u << (c & 31); m.hp_list[nh] = c; nh++; }
       for (int e = 0; e < k; e++) {
         te++;
         if (p.sim_edge[(int64_t)m.par[(int64_t)c * MP + e] + (int64_t)c * P]) ag++;
@@ -430,7 +446,7 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
       const int idx = (int)(s.n_haspar * u);
       BN_U(u);
       if (!ovf) {
-        c = select_kth(m.haspar, p.W, idx);
+        c = m.hp_list[idx];
         e = (int)(m.npar[c] * u);
         j = m.par[(int64_t)c * MP + e];
       }
@@ -457,6 +473,100 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
   }
 #undef BN_U
   Warp::sync();
+  return n;
+}
+
+// ---------------------------------------------------------------------------
+// Phase A, lane-parallel.  The only sequential dependence between iterations is the stream
+// position (each iteration consumes a data-dependent number of uniforms) and the stale
+// `valid` flag.  So lane l replays the iteration that WOULD start at position pos + l
+// (move type, rejection-sampled child/parent, cycle test, uniforms consumed); a short
+// pointer walk then picks the records that are real iteration starts.  One round yields
+// ~32/5 iterations for the latency of one.  Requires TotalEdges >= 4 so that the
+// `TotalEdges < 3` branch of src/bayesnet_mcmc.cpp:48 cannot fire inside the window.
+// ---------------------------------------------------------------------------
+BN_HD int phase_a_fast(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
+                       const RngStream& rng, WindowSlots& ws, int want, int* overflow) {
+  const int P = p.P, MP = p.max_par, l = Warp::lane();
+  const int64_t hi = rng.gen_hi;
+  int64_t pos = s.read_pos;
+  int v = s.valid, n = 0;
+  *overflow = 0;
+  bool stop = false;
+  while (n < want && !stop) {
+    {
+      int64_t i = pos + l;
+      int ovf = 0, type, c = 0, j = 0, e = -1, cyc = 0;
+      double u;
+#define BN_UAT(dst)                                    \
+  do {                                                 \
+    if (i >= hi) { ovf = 1; dst = 0.75; }              \
+    else dst = rng.ubuf[i & (RNG_CAP - 1)];            \
+    i++;                                               \
+  } while (0)
+      BN_UAT(u);
+      if (u > 0.5) {
+        type = 1;
+        for (;;) {
+          BN_UAT(u);
+          c = (int)(P * u);
+          if (ovf || (p.node_type[c] != 1 && m.npar[c] < MP)) break;
+        }
+        const int kc = ovf ? 0 : m.npar[c];
+        const int* pc = m.par + (int64_t)c * MP;
+        for (;;) {
+          BN_UAT(u);
+          j = (int)(P * u);
+          if (ovf) break;
+          int ok = (p.node_type[j] != 2 && j != c);
+          for (int q = 0; q < kc; q++) if (pc[q] == j) ok = 0;
+          if (ok) break;
+        }
+        if (!ovf) cyc = (j == c || test_bit(m.anc + (int64_t)j * p.Ws, c)) ? 1 : 0;
+      } else {
+        type = 2;
+        BN_UAT(u);  // drawn and discarded (src/network.h:309)
+        BN_UAT(u);
+        const int idx = (int)(s.n_haspar * u);
+        BN_UAT(u);
+        if (!ovf) {
+          c = m.hp_list[idx];
+          e = (int)(m.npar[c] * u);
+          j = m.par[(int64_t)c * MP + e];
+        }
+      }
+#undef BN_UAT
+      ws.t_type[l] = (signed char)type; ws.t_c[l] = c; ws.t_j[l] = j; ws.t_e[l] = e;
+      ws.t_cyc[l] = (signed char)cyc; ws.t_ovf[l] = (signed char)ovf;
+      ws.t_consumed[l] = (int)(i - (pos + l));
+    }
+    Warp::sync();
+    int k = 0;
+    while (n < want && k < Warp::NL) {
+      if (ws.t_ovf[k]) { *overflow = (n == 0); stop = true; break; }
+      const int type = ws.t_type[k];
+      const int valid = (type == 1) ? !ws.t_cyc[k] : v;
+      const int cons = ws.t_consumed[k];
+      double ua = 0.0;
+      if (valid) {
+        const int64_t ap = pos + k + cons;
+        if (ap >= hi) { *overflow = (n == 0); stop = true; break; }
+        ua = rng.ubuf[ap & (RNG_CAP - 1)];
+      }
+      const int len = cons + (valid ? 1 : 0);
+      if (l == 0) {
+        ws.child[n] = ws.t_c[k]; ws.parent[n] = ws.t_j[k]; ws.pos[n] = ws.t_e[k];
+        ws.type[n] = (signed char)type; ws.valid[n] = (signed char)valid;
+        ws.te_m[n] = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
+        ws.pos_after[n] = pos + k + len; ws.u_acc[n] = ua;
+      }
+      v = valid;
+      k += len;
+      n++;
+    }
+    pos += k;
+    Warp::sync();
+  }
   return n;
 }
 
@@ -528,7 +638,7 @@ BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars&
 // Commit: counters, trace rows, and the accepted move if any (warp-uniform).
 // ---------------------------------------------------------------------------
 BN_HD void write_row(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
-                     const WindowSlots& ws, int i) {
+                     const WindowSlots& ws, int i, int additions, int deletions) {
   if (!s.gll_ok) { s.gll = sum_base(p, m); s.gll_ok = 1; }
   if (s.n_rows < p.trace_capacity) {
     if (Warp::lane() == 0) {
@@ -537,8 +647,8 @@ BN_HD void write_row(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t
       m.t_changed[r] = ws.child[i];
       m.t_movetype[r] = ws.type[i];
       m.t_gll[r] = s.gll;
-      m.t_add[r] = s.proposed[1] - s.reject[1];
-      m.t_del[r] = s.proposed[2] - s.reject[2];
+      m.t_add[r] = additions;
+      m.t_del[r] = deletions;
       m.t_fn[r] = ws.fn_m[i];
       m.t_fp[r] = ws.fp_m[i];
     }
@@ -558,10 +668,14 @@ BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_
   if (ws.type[i] == 1) {
     if (l == 0) {
       pc[k] = j; bc[k] = (int)first_counted; m.npar[c] = k + 1;
-      if (k == 0) m.haspar[c >> 5] |= 1u << (c & 31);
       m.base[c] = ws.new_score[i];
     }
-    if (k == 0) s.n_haspar++;
+    if (k == 0) {
+      Warp::sync();
+      hp_insert(m, s.n_haspar, c);  // rank from the bitset BEFORE c's bit is set
+      if (l == 0) m.haspar[c >> 5] |= 1u << (c & 31);
+      s.n_haspar++;
+    }
     s.te_true++; s.agree_true += ag;
     Warp::sync();
     anc_after_add(p, m, j, c);
@@ -575,10 +689,14 @@ BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_
       for (int e = del; e + 1 < k; e++) { pc[e] = pc[e + 1]; bc[e] = bc[e + 1]; }
       pc[k - 1] = -1;
       m.npar[c] = k - 1;
-      if (k == 1) m.haspar[c >> 5] &= ~(1u << (c & 31));
       m.base[c] = ws.new_score[i];
     }
-    if (k == 1) s.n_haspar--;
+    if (k == 1) {
+      Warp::sync();
+      hp_remove(m, s.n_haspar, c);
+      if (l == 0) m.haspar[c >> 5] &= ~(1u << (c & 31));
+      s.n_haspar--;
+    }
     s.te_true--; s.agree_true -= ag;
     Warp::sync();
     anc_after_delete(p, m, c);
@@ -597,22 +715,51 @@ BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_
 // Commit slots [0, ncommit): all but possibly the last are rejections/invalid.
 BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const WindowSlots& ws,
                   int ncommit) {
-  for (int i = 0; i < ncommit; i++) {
+  // One lane per slot: the counters are ballots + popcounts instead of a sequential loop.
+  // Only the last committed slot can be an acceptance; rows logged before it see the
+  // pre-move graph, its own row (if any) the post-move graph.
+  const int l = Warp::lane();
+  for (int i0 = 0; i0 < ncommit; i0 += Warp::NL) {
+    const int i = i0 + l;
+    const bool in = i < ncommit;
     const int64_t it = s.iter + i;
-    const int type = ws.type[i];
-    if (ws.valid[i]) {
-      s.valid_iters++;
-      s.alg_bytes += 4 * (int64_t)(ws.kk[i] + 1) * (ws.kk[i] + 2) + 8;
-      if (it >= p.drop) s.proposed[type]++;  // src/network.h:331
-      if (ws.nonpd[i]) s.n_nonpd++;
-      if (ws.accept[i]) {
-        apply_move(p, m, s, it, ws, i);
-      } else if (it >= p.drop) {
-        s.reject[type]++;  // src/bayesnet_mcmc.cpp:58
-      }
-      if (it % p.output_every == 0) write_row(p, m, s, it, ws, i);  // :63-65
-    } else {
-      s.reject[0]++;  // notValid(), src/network.h:434-437 (not guarded by drop)
+    const bool valid = in && ws.valid[in ? i : 0];
+    const int type = in ? ws.type[i] : 0;
+    const bool counted = valid && it >= p.drop;  // src/network.h:331, src/bayesnet_mcmc.cpp:58
+    const bool acc = valid && ws.accept[in ? i : 0];
+    const uint32_t m_valid = Warp::ballot(valid);
+    const uint32_t m_inval = Warp::ballot(in && !valid);
+    const uint32_t m_p1 = Warp::ballot(counted && type == 1);
+    const uint32_t m_p2 = Warp::ballot(counted && type == 2);
+    const uint32_t m_r1 = Warp::ballot(counted && type == 1 && !acc);
+    const uint32_t m_r2 = Warp::ballot(counted && type == 2 && !acc);
+    const uint32_t m_npd = Warp::ballot(valid && ws.nonpd[in ? i : 0]);
+    const uint32_t m_acc = Warp::ballot(acc);
+    const uint32_t m_log = Warp::ballot(valid && (it % p.output_every == 0));  // :63-65
+    const int kk = valid ? ws.kk[i] : 0;
+    const int bytes = Warp::sum(valid ? 4 * (kk + 1) * (kk + 2) + 8 : 0);
+    // rows of rejected iterations (pre-move graph), in order
+    uint32_t lg = m_log & ~m_acc;
+    while (lg) {
+      const int b = ffs32(lg) - 1;
+      lg &= lg - 1;
+      const uint32_t upto = (b == 31) ? 0xffffffffu : ((2u << b) - 1u);
+      write_row(p, m, s, s.iter + i0 + b, ws, i0 + b,
+                (s.proposed[1] + popc32(m_p1 & upto)) - (s.reject[1] + popc32(m_r1 & upto)),
+                (s.proposed[2] + popc32(m_p2 & upto)) - (s.reject[2] + popc32(m_r2 & upto)));
+    }
+    s.valid_iters += popc32(m_valid);
+    s.alg_bytes += bytes;
+    s.proposed[1] += popc32(m_p1); s.proposed[2] += popc32(m_p2);
+    s.reject[0] += popc32(m_inval);  // notValid(), src/network.h:434-437 (not guarded by drop)
+    s.reject[1] += popc32(m_r1); s.reject[2] += popc32(m_r2);
+    s.n_nonpd += popc32(m_npd);
+    if (m_acc) {
+      const int b = ffs32(m_acc) - 1;  // == the last committed slot
+      apply_move(p, m, s, s.iter + i0 + b, ws, i0 + b);
+      if (m_log & m_acc)
+        write_row(p, m, s, s.iter + i0 + b, ws, i0 + b, s.proposed[1] - s.reject[1],
+                  s.proposed[2] - s.reject[2]);
     }
   }
   const int last = ncommit - 1;
@@ -638,7 +785,9 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     int want = s.win;
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     int overflow = 0;
-    const int n = phase_a(p, m, s, rng, ws, want, &overflow);
+    // the lane-parallel replay needs `TotalEdges < 3` to be impossible inside the window
+    const int n = (s.te_true >= 4 && s.te_m >= 3) ? phase_a_fast(p, m, s, rng, ws, want, &overflow)
+                                                  : phase_a(p, m, s, rng, ws, want, &overflow);
     if (n == 0) {
       s.status = 4;  // BN_ERR_NO_LEGAL_PROPOSAL
       break;

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace
   m.base = sm.off_base >= 0 ? (double*)(dyn_smem + sm.off_base) : w.base + ch * P;
   m.anc = sm.off_anc >= 0 ? (uint32_t*)(dyn_smem + sm.off_anc) : w.anc + ch * P * (int64_t)p.Ws;
   m.haspar = sm.off_haspar >= 0 ? (uint32_t*)(dyn_smem + sm.off_haspar) : w.haspar + ch * W;
+  m.hp_list = sm.off_hplist >= 0 ? (int*)(dyn_smem + sm.off_hplist) : w.hp_list + ch * P;
   m.scratch = sm.off_scratch >= 0 ? (int*)(dyn_smem + sm.off_scratch) : w.scratch + (int64_t)ch * w.scratch_n;
   const int64_t cap = p.trace_capacity;
   m.t_iter = w.t_iter + ch * cap; m.t_changed = w.t_changed + ch * cap;
@@ -97,6 +98,7 @@ static ChainSmemPlan plan_chain_smem(ChainParams& p, int scratch_n, int budget) 
   sm.off_npar = place(P * 4);
   sm.off_base = place(P * 8);
   sm.off_haspar = place(W * 4);
+  sm.off_hplist = place(P * 4);
   sm.off_par = place(P * MP * 4);
   sm.off_scratch = place((int64_t)scratch_n * 4);
   // in shared memory, keep the row stride off a multiple of 32 words so that the column

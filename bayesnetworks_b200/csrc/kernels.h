@@ -9,6 +9,7 @@ namespace bn {
 
 struct ChainWorkspace {  // arrays over all chains of a run (device memory)
   int* par; int* npar; int* born; double* base;
+  int* hp_list;
   uint32_t* anc; uint32_t* haspar;   // anc rows are anc_stride(W) words apart in global memory
   int* scratch; int scratch_n;        // 4 * scratch_stride(P) ints per chain
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
@@ -20,7 +21,7 @@ struct ChainWorkspace {  // arrays over all chains of a run (device memory)
 // One chain = one CTA, so the hot state (parent lists, scores, ancestor bitsets) sits
 // ~30 cycles away instead of an L2 round trip; arrays that do not fit stay in global.
 struct ChainSmemPlan {
-  int off_types, off_npar, off_base, off_haspar, off_par, off_scratch, off_anc;
+  int off_types, off_npar, off_base, off_haspar, off_hplist, off_par, off_scratch, off_anc;
   int total_bytes;
 };
 

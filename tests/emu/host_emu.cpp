@@ -30,7 +30,7 @@ extern "C" int emu_run_chain(
   p.prior_par = prior_par; p.prior_npar = prior_npar;
 
   std::vector<int> par((size_t)P * max_par), npar(P), born((size_t)P * max_par);
-  std::vector<int> scratch((size_t)4 * scratch_stride(P));
+  std::vector<int> scratch((size_t)4 * scratch_stride(P)), hp_list(P);
   std::vector<double> base(P);
   std::vector<uint32_t> anc_store((size_t)P * p.Ws + 4), haspar(p.W);
   uint32_t* anc = (uint32_t*)(((uintptr_t)anc_store.data() + 15) & ~(uintptr_t)15);
@@ -39,7 +39,7 @@ extern "C" int emu_run_chain(
   ChainMem m;
   m.par = par.data(); m.npar = npar.data(); m.born = born.data(); m.base = base.data();
   m.anc = anc; m.haspar = haspar.data();
-  m.scratch = scratch.data();
+  m.scratch = scratch.data(); m.hp_list = hp_list.data();
   m.t_iter = t_iter; m.t_changed = t_changed; m.t_movetype = t_movetype; m.t_gll = t_gll;
   m.t_add = t_add; m.t_del = t_del; m.t_fn = t_fn; m.t_fp = t_fp;
   m.moves = moves; m.edge_freq = edge_freq;
