@@ -268,8 +268,11 @@ extern "C" int bn_create(const double* X, int n_samples, int P, const int* src, 
   cudaError_t e = pool_alloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
   if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the device copy of X"); }
   // column p of the R matrix is contiguous: one pitched copy into the padded buffer
-  e = cudaMemcpy2DAsync(dXc, (size_t)pl.ld_centered * 8, X, (size_t)n_samples * 8, (size_t)n_samples * 8,
-                        (size_t)P, cudaMemcpyHostToDevice, c->stream);
+  if (pl.ld_centered == n_samples)
+    e = cudaMemcpyAsync(dXc, X, (size_t)n_samples * P * 8, cudaMemcpyHostToDevice, c->stream);
+  else
+    e = cudaMemcpy2DAsync(dXc, (size_t)pl.ld_centered * 8, X, (size_t)n_samples * 8, (size_t)n_samples * 8,
+                          (size_t)P, cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "H2D copy of X: %s", cudaGetErrorString(e));
   if (!rc) rc = ctx_build_gram(c, dXc, pl.ld_centered, dXc, pl);  // centred in place
   pool_free(dXc);

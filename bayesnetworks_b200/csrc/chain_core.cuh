@@ -84,8 +84,9 @@ struct WindowSlots {  // shared memory on the device
   double u_acc[WIN], new_score[WIN];
   signed char type[WIN], valid[WIN], do_check[WIN], accept[WIN], nonpd[WIN];
   // lane-parallel draw replay: outcome of a slot that would start at stream position pos + lane
-  int t_c[WIN], t_j[WIN], t_e[WIN], t_consumed[WIN];
-  signed char t_type[WIN], t_cyc[WIN], t_ovf[WIN];
+  int t_c[WIN], t_j[WIN], t_e[WIN];
+  int t_rec[WIN];   // consumed | type << 8 | cyc << 9 | ovf << 10
+  int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
 BN_HD bool test_bit(const uint32_t* row, int b) { return (row[b >> 5] >> (b & 31)) & 1u; }
@@ -183,12 +184,16 @@ BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 32; }
 // nodes that have c as an ancestor (ascending), optionally preceded by c itself
 BN_HD int collect_desc(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list) {
   const int l = Warp::lane(), P = p.P;
+  const uint32_t Ws = (uint32_t)p.Ws, cb = (uint32_t)c & 31u;
+  const uint32_t* col = m.anc + (c >> 5);  // word (c >> 5) of every row
+  const uint32_t lt = (1u << l) - 1u;
   int n = 0;
   for (int d0 = 0; d0 < P; d0 += Warp::NL) {
     const int d = d0 + l;
-    const int flag = (d < P) && ((include_self && d == c) || test_bit(m.anc + (int64_t)d * p.Ws, c));
+    int flag = 0;
+    if (d < P) flag = ((col[(uint32_t)d * Ws] >> cb) & 1u) | ((include_self && d == c) ? 1 : 0);
     const uint32_t mask = Warp::ballot(flag);
-    if (flag) list[n + popc32(mask & ((1u << l) - 1u))] = d;
+    if (flag) list[n + popc32(mask & lt)] = d;
     n += popc32(mask);
   }
   Warp::sync();
@@ -217,15 +222,31 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
   const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr;
   int* list = m.scratch;
   const int n = collect_desc(p, m, c, 1, list);
-  const U4* aj = (const U4*)(m.anc + (int64_t)j * p.Ws);
-  for (int r0 = 0; r0 < n; r0 += g.rpp) {
-    const int r = r0 + sub;
-    if (r < n) {
-      U4* ad = (U4*)(m.anc + (int64_t)list[r] * p.Ws);
-      for (int ch = li; ch < g.chunks; ch += g.lpr) {
-        U4 v = or4(ad[ch], aj[ch]);
-        if (ch == (j >> 7)) v = with_bit(v, j & 127);
-        ad[ch] = v;
+  const U4* aj = (const U4*)(m.anc + (uint32_t)j * (uint32_t)p.Ws);
+  if (g.chunks <= g.lpr) {
+    // one 128-bit chunk per lane (up to 4,096 nodes): the source chunk stays in registers
+    U4 a = {0u, 0u, 0u, 0u};
+    if (li < g.chunks) {
+      a = aj[li];
+      if (li == (j >> 7)) a = with_bit(a, j & 127);
+    }
+    for (int r0 = 0; r0 < n; r0 += g.rpp) {
+      const int r = r0 + sub;
+      if (r < n && li < g.chunks) {
+        U4* ad = (U4*)(m.anc + (uint32_t)list[r] * (uint32_t)p.Ws) + li;
+        *ad = or4(*ad, a);
+      }
+    }
+  } else {
+    for (int r0 = 0; r0 < n; r0 += g.rpp) {
+      const int r = r0 + sub;
+      if (r < n) {
+        U4* ad = (U4*)(m.anc + (int64_t)list[r] * p.Ws);
+        for (int ch = li; ch < g.chunks; ch += g.lpr) {
+          U4 v = or4(ad[ch], aj[ch]);
+          if (ch == (j >> 7)) v = with_bit(v, j & 127);
+          ad[ch] = v;
+        }
       }
     }
   }
@@ -536,33 +557,42 @@ BN_HD int phase_a_fast(const ChainParams& p, const ChainMem& m, const ChainScala
         }
       }
 #undef BN_UAT
-      ws.t_type[l] = (signed char)type; ws.t_c[l] = c; ws.t_j[l] = j; ws.t_e[l] = e;
-      ws.t_cyc[l] = (signed char)cyc; ws.t_ovf[l] = (signed char)ovf;
-      ws.t_consumed[l] = (int)(i - (pos + l));
+      ws.t_c[l] = c; ws.t_j[l] = j; ws.t_e[l] = e;
+      ws.t_rec[l] = (int)(i - (pos + l)) | ((type - 1) << 8) | (cyc << 9) | (ovf << 10);
     }
     Warp::sync();
+    // walk: which records are real iteration starts (cheap, warp-uniform)
     int k = 0;
+    const int n0 = n, v0 = v;
     while (n < want && k < Warp::NL) {
-      if (ws.t_ovf[k]) { *overflow = (n == 0); stop = true; break; }
-      const int type = ws.t_type[k];
-      const int valid = (type == 1) ? !ws.t_cyc[k] : v;
-      const int cons = ws.t_consumed[k];
-      double ua = 0.0;
-      if (valid) {
-        const int64_t ap = pos + k + cons;
-        if (ap >= hi) { *overflow = (n == 0); stop = true; break; }
-        ua = rng.ubuf[ap & (RNG_CAP - 1)];
-      }
-      const int len = cons + (valid ? 1 : 0);
-      if (l == 0) {
-        ws.child[n] = ws.t_c[k]; ws.parent[n] = ws.t_j[k]; ws.pos[n] = ws.t_e[k];
-        ws.type[n] = (signed char)type; ws.valid[n] = (signed char)valid;
-        ws.te_m[n] = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
-        ws.pos_after[n] = pos + k + len; ws.u_acc[n] = ua;
-      }
+      const int rec = ws.t_rec[k];
+      if (rec & (1 << 10)) { *overflow = (n == 0); stop = true; break; }
+      const int valid = (rec & (1 << 8)) ? v : !((rec >> 9) & 1);
+      const int len = (rec & 0xff) + (valid ? 1 : 0);
+      if (pos + k + len > hi) { *overflow = (n == 0); stop = true; break; }
+      if (l == 0) ws.s_k[n] = k | (valid << 16);
       v = valid;
       k += len;
       n++;
+    }
+    Warp::sync();
+    // emit: one lane per new slot
+    (void)v0;
+    for (int q0 = n0; q0 < n; q0 += Warp::NL) {
+      const int q = q0 + l;
+      if (q < n) {
+        const int sk = ws.s_k[q];
+        const int kk = sk & 0xffff, valid = sk >> 16;
+        const int rec = ws.t_rec[kk];
+        const int type = ((rec >> 8) & 1) + 1;
+        const int cons = rec & 0xff;
+        const int64_t at = pos + kk + cons;
+        ws.child[q] = ws.t_c[kk]; ws.parent[q] = ws.t_j[kk]; ws.pos[q] = ws.t_e[kk];
+        ws.type[q] = (signed char)type; ws.valid[q] = (signed char)valid;
+        ws.te_m[q] = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
+        ws.u_acc[q] = valid ? rng.ubuf[at & (RNG_CAP - 1)] : 0.0;
+        ws.pos_after[q] = at + (valid ? 1 : 0);
+      }
     }
     pos += k;
     Warp::sync();
@@ -795,7 +825,11 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     for (int i = l; i < n; i += Warp::NL) phase_bc<KMAX>(p, m, s, ws, i);
     Warp::sync();
     int first = -1;
-    for (int i = 0; i < n; i++) if (ws.valid[i] && ws.accept[i]) { first = i; break; }
+    for (int i0 = 0; i0 < n && first < 0; i0 += Warp::NL) {
+      const int i = i0 + l;
+      const uint32_t am = Warp::ballot(i < n && ws.valid[i < n ? i : 0] && ws.accept[i < n ? i : 0]);
+      if (am) first = i0 + ffs32(am) - 1;
+    }
     const int ncommit = (first >= 0) ? first + 1 : n;
     commit(p, m, s, ws, ncommit);
     s.windows++;

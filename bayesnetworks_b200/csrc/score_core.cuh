@@ -59,6 +59,14 @@ BN_HD double score_set(const double* __restrict__ C, int64_t ldc, int c,
   return -((double)n_samples / 2.0) * log(resid2 / syy);
 }
 
+BN_HD double rsqrt_f64(double d) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(d);
+#else
+  return 1.0 / sqrt(d);
+#endif
+}
+
 // Register-resident variant for small parent limits (K <= 8): every index is a
 // compile-time constant after unrolling, so the factor lives in registers, the gathers
 // issue back to back (one L2 round trip instead of one per row) and the divisions
@@ -92,7 +100,7 @@ BN_HD double score_set_small(const double* __restrict__ C, int64_t ldc, int c, c
 #pragma unroll
       for (int t = 0; t < i; t++) d -= L[i * (i + 1) / 2 + t] * L[i * (i + 1) / 2 + t];
       if (!(d > 0.0)) { bad = true; d = 1.0; }
-      const double r = 1.0 / sqrt(d);
+      const double r = rsqrt_f64(d);
       rinv[i] = r;
       double acc = z[i];
 #pragma unroll

@@ -233,7 +233,10 @@ def run_ours(a):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
+            t0 = time.perf_counter()
             fn()
+            if os.environ.get("BN_BENCH_VERBOSE"):
+                print(f"[bench] {fn.__name__}: {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
