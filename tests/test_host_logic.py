@@ -126,7 +126,7 @@ def _rmt_state(seed):
     return out[1:].copy()
 
 
-def _emu_run(lib, dataset, max_par, n_iter, output, kind, seeds, init=2, drop=0):
+def _emu_run(lib, dataset, max_par, n_iter, output, kind, seeds, init=2, drop=0, phi=1.0, omega=6.9):
     X, src, tgt, nt = dataset["X"], dataset["source"], dataset["target"], dataset["node_type"]
     N, P = X.shape
     _, Cm = centered_stats(X)
@@ -149,7 +149,7 @@ def _emu_run(lib, dataset, max_par, n_iter, output, kind, seeds, init=2, drop=0)
     dp, ip, up = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_ubyte)
     rc = lib.emu_run_chain(
         P, max_par, N, Cm.ctypes.data_as(dp), ntu.ctypes.data_as(up), sim.ctypes.data_as(up),
-        int(len(src)), C.c_double(1.0), C.c_double(6.9), init, drop, n_iter, output,
+        int(len(src)), C.c_double(phi), C.c_double(omega), init, drop, n_iter, output,
         ppar.ctypes.data_as(ip), pnpar.ctypes.data_as(ip), kind, sd.ctypes.data_as(ip),
         mt.ctypes.data_as(C.POINTER(C.c_uint)), None, C.c_long(0), cap,
         ti[0].ctypes.data_as(ip), ti[1].ctypes.data_as(ip), ti[2].ctypes.data_as(ip),
@@ -197,6 +197,31 @@ def test_chain_core_every_iteration_and_tabulation(emu_lib, dataset, golden):
     r0 = _emu_run(emu_lib, dataset, 8, 2000, 1, 1, (99,), init=0)
     for k in INT_COLS:
         assert np.array_equal(r0[k], golden[f"every_init0_{k}"]), k
+
+
+@pytest.mark.parametrize("max_par,omega", [(5, 0.5), (12, 0.2)])
+def test_chain_core_dense_synthetic_vs_oracle(emu_lib, oracle, max_par, omega):
+    """Dense graphs (weak size penalty): many accepted deletions, large descendant sets, nodes
+    at the parent limit -- the general ancestor-recompute path, the hp_list maintenance and the
+    MaxPar masks, against the oracle (which does a BFS per proposal like the reference)."""
+    from bayesnetworks_b200.synth import make_dag, make_prior, simulate_numpy
+    from oracle.oracle import RNG_WH
+    P, N, n_iter = 40, 500, 20000
+    dag = make_dag(P, seed=5)
+    g = make_prior(dag, max_par=max_par, seed=6)
+    X = simulate_numpy(dag, N, seed=7)
+    nt = g.node_type_codes()
+    ref = oracle.mcmc(X, g.source, g.target, nt, max_par=max_par, phi=1.0, omega=omega, n_iter=n_iter,
+                      output=7, rng_kind=RNG_WH, seeds=(123, 456, 789))
+    ds = dict(X=X, source=g.source, target=g.target, node_type=nt)
+    r = _emu_run(emu_lib, ds, max_par, n_iter, 7, 0, (123, 456, 789), omega=omega)
+    assert r["rc"] == 0
+    for k in INT_COLS:
+        assert np.array_equal(r[k], getattr(ref, k)), k
+    np.testing.assert_allclose(r["globalLL"], ref.globalLL, rtol=1e-9, atol=1e-9 * N / 2)
+    assert np.array_equal(r["moves"], ref.accepted_moves())
+    assert int(r["cnt"][0]) == ref.uniforms
+    assert ref.deletions[-1] > 200 and ref.final_npar.max() == max_par  # the regime is exercised
 
 
 def test_device_rng_core_matches_goldens(emu_lib, golden):
