@@ -54,6 +54,7 @@ struct ChainMem {  // per-chain global memory
   uint32_t* haspar;    // [W] nodes with >= 1 parent (bitset)
   int* hp_list;        // [P] the same set as an ascending list (CurrOutputs, src/network.h:311-316)
   int* scratch;        // [4 * scratch_stride(P)] lists / keys / histogram for the ancestor updates
+  volatile int* helper;  // device only: command block of the CTA's helper warps (null = none)
   // outputs
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
   int* t_add; int* t_del; int* t_fn; int* t_fp;
@@ -182,22 +183,26 @@ BN_HD int atomic_fetch_inc(int* p) {
 BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 32; }
 
 // nodes that have c as an ancestor (ascending), optionally preceded by c itself
-BN_HD int collect_desc(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list) {
-  const int l = Warp::lane(), P = p.P;
+BN_HD int collect_desc_range(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list,
+                             int d_lo, int d_hi) {
+  const int l = Warp::lane();
   const uint32_t Ws = (uint32_t)p.Ws, cb = (uint32_t)c & 31u;
   const uint32_t* col = m.anc + (c >> 5);  // word (c >> 5) of every row
   const uint32_t lt = (1u << l) - 1u;
   int n = 0;
-  for (int d0 = 0; d0 < P; d0 += Warp::NL) {
+  for (int d0 = d_lo; d0 < d_hi; d0 += Warp::NL) {
     const int d = d0 + l;
     int flag = 0;
-    if (d < P) flag = ((col[(uint32_t)d * Ws] >> cb) & 1u) | ((include_self && d == c) ? 1 : 0);
+    if (d < d_hi) flag = ((col[(uint32_t)d * Ws] >> cb) & 1u) | ((include_self && d == c) ? 1 : 0);
     const uint32_t mask = Warp::ballot(flag);
     if (flag) list[n + popc32(mask & lt)] = d;
     n += popc32(mask);
   }
   Warp::sync();
   return n;
+}
+BN_HD int collect_desc(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list) {
+  return collect_desc_range(p, m, c, include_self, list, 0, p.P);
 }
 
 // anc[d] = union over the parents q of d of (anc[q] u {q}); all lanes, one row
@@ -217,11 +222,11 @@ BN_HD void recompute_row(const ChainParams& p, ChainMem& m, int d, int chunks) {
 }
 
 // after adding parent j to child c: every node in {c} u desc(c) gains anc[j] u {j}
-BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
+// rows [d_lo, d_hi) of the update: one warp's share (the whole range on the host)
+BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, int* list, int d_lo, int d_hi) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr;
-  int* list = m.scratch;
-  const int n = collect_desc(p, m, c, 1, list);
+  const int n = collect_desc_range(p, m, c, 1, list, d_lo, d_hi);
   const U4* aj = (const U4*)(m.anc + (uint32_t)j * (uint32_t)p.Ws);
   if (g.chunks <= g.lpr) {
     // one 128-bit chunk per lane (up to 4,096 nodes): the source chunk stays in registers
@@ -252,6 +257,54 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
   }
   Warp::sync();
 }
+
+// The CTA of a chain has HELPER_WARPS extra warps parked on a named barrier; they take an
+// equal share of the rows of an ancestor update (the scan and the ORs are independent per row).
+constexpr int HELPER_WARPS = 3;
+enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1 };
+BN_HD void helper_row_range(int P, int part, int nparts, int* d_lo, int* d_hi) {
+  const int per = ((P + nparts - 1) / nparts + 31) / 32 * 32;
+  *d_lo = part * per < P ? part * per : P;
+  *d_hi = (part + 1) * per < P ? (part + 1) * per : P;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void cta_bar(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"((HELPER_WARPS + 1) * 32) : "memory");
+}
+#endif
+
+BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
+#if defined(__CUDA_ARCH__)
+  if (m.helper) {
+    if (Warp::lane() == 0) { m.helper[1] = j; m.helper[2] = c; m.helper[0] = HELPER_ANC_ADD; }
+    Warp::sync();
+    cta_bar(1);
+    int lo, hi;
+    helper_row_range(p.P, 0, HELPER_WARPS + 1, &lo, &hi);
+    anc_add_part(p, m, j, c, m.scratch, lo, hi);
+    cta_bar(2);
+    return;
+  }
+#endif
+  anc_add_part(p, m, j, c, m.scratch, 0, p.P);
+}
+
+#if defined(__CUDACC__)
+// body of a helper warp (warp index 1..HELPER_WARPS of the chain's CTA)
+__device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem& m, int part) {
+  for (;;) {
+    cta_bar(1);
+    const int op = m.helper[0];
+    if (op == HELPER_EXIT) break;
+    if (op == HELPER_ANC_ADD) {
+      int lo, hi;
+      helper_row_range(p.P, part, HELPER_WARPS + 1, &lo, &hi);
+      anc_add_part(p, m, m.helper[1], m.helper[2], m.scratch + part * scratch_stride(p.P), lo, hi);
+    }
+    cta_bar(2);
+  }
+}
+#endif
 
 // after removing a parent of child c (par[c] already updated).  If the remaining parents
 // still reach everything c reached, nothing changes anywhere (the common case in a graph

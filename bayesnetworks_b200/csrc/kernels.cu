@@ -13,11 +13,13 @@ namespace bn {
 // this CTA touches it); the Gram is read with L2-only loads.
 // ---------------------------------------------------------------------------
 template <int KMAX>
-__global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
+__global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
                                                    ChainSmemPlan sm, ChainResult* __restrict__ results) {
   __shared__ double ubuf[RNG_CAP];
   __shared__ WindowSlots ws;
+  __shared__ int helper_cmd[4];
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x;
   const int64_t P = p.P, MP = p.max_par, W = p.W;
 
@@ -39,6 +41,7 @@ __global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace
   m.t_fn = w.t_fn + ch * cap; m.t_fp = w.t_fp + ch * cap;
   m.moves = w.moves ? w.moves + (int64_t)ch * p.moves_capacity * 4 : nullptr;
   m.edge_freq = w.edge_freq ? w.edge_freq + ch * P * P : nullptr;
+  m.helper = helper_cmd;
 
   RngStream rng;
   if (ra.kind == RNG_WH)
@@ -50,22 +53,29 @@ __global__ void __launch_bounds__(32) chain_kernel(ChainParams p, ChainWorkspace
 
   ChainParams pp = p;
   if (!m.moves) pp.moves_capacity = 0;
+  if (warp != 0) {  // helper warps: parked on a named barrier until the chain needs them
+    helper_loop(pp, m, warp);
+    return;
+  }
   if (sm.off_types >= 0) {
     uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);
-    for (int i = threadIdx.x; i < p.P; i += 32) t[i] = p.node_type[i];
+    for (int i = lane; i < p.P; i += 32) t[i] = p.node_type[i];
     __syncwarp();
     pp.node_type = t;
   }
   ChainScalars s;
   run_chain<KMAX>(pp, m, s, rng, ws);
+  if (lane == 0) helper_cmd[0] = HELPER_EXIT;
+  __syncwarp();
+  cta_bar(1);
 
   // final graph back to global memory when it lived in shared memory
   if (m.par != g_par)
-    for (int64_t i = threadIdx.x; i < P * MP; i += 32) g_par[i] = m.par[i];
+    for (int64_t i = lane; i < P * MP; i += 32) g_par[i] = m.par[i];
   if (m.npar != g_npar)
-    for (int64_t i = threadIdx.x; i < P; i += 32) g_npar[i] = m.npar[i];
+    for (int64_t i = lane; i < P; i += 32) g_npar[i] = m.npar[i];
 
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     ChainResult& r = results[ch];
     r.uniforms = s.read_pos;
     r.valid_iters = s.valid_iters;
@@ -124,7 +134,7 @@ static const char* launch_chains_t(ChainParams p, const ChainWorkspace& w, const
   if (cudaFuncSetAttribute(chain_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            sm.total_bytes) != cudaSuccess)
     return "cudaFuncSetAttribute(chain_kernel) failed";
-  chain_kernel<KMAX><<<n_chains, 32, sm.total_bytes, stream>>>(p, w, ra, sm, d_results);
+  chain_kernel<KMAX><<<n_chains, (HELPER_WARPS + 1) * 32, sm.total_bytes, stream>>>(p, w, ra, sm, d_results);
   return nullptr;
 }
 

@@ -39,7 +39,7 @@ extern "C" int emu_run_chain(
   ChainMem m;
   m.par = par.data(); m.npar = npar.data(); m.born = born.data(); m.base = base.data();
   m.anc = anc; m.haspar = haspar.data();
-  m.scratch = scratch.data(); m.hp_list = hp_list.data();
+  m.scratch = scratch.data(); m.hp_list = hp_list.data(); m.helper = nullptr;
   m.t_iter = t_iter; m.t_changed = t_changed; m.t_movetype = t_movetype; m.t_gll = t_gll;
   m.t_add = t_add; m.t_del = t_del; m.t_fn = t_fn; m.t_fp = t_fp;
   m.moves = moves; m.edge_freq = edge_freq;
