@@ -235,7 +235,7 @@ __device__ __forceinline__ void border_row(const double* __restrict__ C, int64_t
 #pragma unroll
         for (int t = 0; t < KMAX; t++)
           if (t < i) acc -= Li[t] * w[t];
-        acc /= Li[i];
+        acc *= Li[i];  // the diagonal slot holds 1 / L[i][i]
         w[i] = acc;
         dj -= acc * acc;
         ej -= acc * zrow[i];
@@ -246,7 +246,7 @@ __device__ __forceinline__ void border_row(const double* __restrict__ C, int64_t
       double acc = __ldcg(C + (int64_t)S[i] * ldc + j);
       const double* Li = A + i * (i + 1) / 2;
       for (int t = 0; t < i; t++) acc -= Li[t] * w[t];
-      acc /= Li[i];
+      acc *= Li[i];
       w[i] = acc;
       dj -= acc * acc;
       ej -= acc * zrow[i];
@@ -302,9 +302,13 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp)
     }
     __syncwarp();
   }
+  // the candidate rows multiply by the reciprocal pivots
+  for (int i = lane; i < k; i += 32) A[i * (i + 1) / 2 + i] = 1.0 / A[i * (i + 1) / 2 + i];
+  __syncwarp();
   const double n = (double)sp.n_samples;
   const double syy = Ccc / (n - 1.0);
   const double rss = A[tri - 1];
+  const double add_scale = 1.0 / ((n - (double)k - 2.0) * syy);  // 1 / (dof * SYY) of an addition
   const double* zrow = A + k * (k + 1) / 2;
   const double base = pd ? -(n / 2.0) * log((rss / (n - (double)k - 1.0)) / syy) : -INFINITY;
   if (lane == 0 && sp.out_base) sp.out_base[wg] = base;
@@ -315,6 +319,10 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp)
   const uint8_t type_c = sp.node_type[c];
   const bool can_add = (type_c != 1) && (k < MP);
   const double nan = __longlong_as_double(0x7ff8000000000000ULL);
+  // NewLogPrior of an addition only depends on whether the new edge is in the prior graph
+  const double add_prior0 = prior_value(sp.phi, sp.omega, (te + 1 - ag) + (sp.n_sim_edges - ag), te + 1);
+  const double add_prior1 = prior_value(sp.phi, sp.omega, (te + 1 - (ag + 1)) + (sp.n_sim_edges - (ag + 1)), te + 1);
+  const uint8_t* sim_row = sp.sim_edge + (int64_t)c * P;
   double* out_s = sp.out_score ? sp.out_score + wg * P : nullptr;
   double* out_h = sp.out_log_hr ? sp.out_log_hr + wg * P : nullptr;
 
@@ -327,6 +335,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp)
     if (member) continue;  // deletions below
     double sc = nan, hr = nan;
     if (can_add && j != c && sp.node_type[j] != 2) {
+      const int a1 = sim_row[j];
       if (!pd) {
         sc = -INFINITY;
       } else {
@@ -335,15 +344,12 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp)
         border_row<KMAX>(C, ldc, S, k, j, A, zrow, dj, ej);
         if (dj > 0.0) {
           const double rss_new = rss - ej * ej / dj;
-          sc = -(n / 2.0) * log((rss_new / (n - (double)k - 2.0)) / syy);
+          sc = -(n / 2.0) * log(rss_new * add_scale);
         } else {
           sc = -INFINITY;
         }
       }
-      const int a1 = sp.sim_edge[(int64_t)j + (int64_t)c * P] ? 1 : 0;
-      const int te_n = te + 1, ag_n = ag + a1;
-      const double new_prior = prior_value(sp.phi, sp.omega, (te_n - ag_n) + (sp.n_sim_edges - ag_n), te_n);
-      hr = sub_rn(add_rn(sub_rn(sc, base), new_prior), old_prior);
+      hr = sub_rn(add_rn(sub_rn(sc, base), a1 ? add_prior1 : add_prior0), old_prior);
     }
     if (out_s) out_s[j] = sc;
     if (out_h) out_h[j] = hr;
