@@ -45,7 +45,8 @@ class Trace(C.Structure):
 class ChainStats(C.Structure):
     _fields_ = [("uniforms", C.c_int64), ("valid_iters", C.c_int64), ("proposed", C.c_int * 3),
                 ("reject", C.c_int * 3), ("n_nonpd", C.c_int), ("total_edges", C.c_int),
-                ("status", C.c_int), ("windows", C.c_int), ("alg_bytes", C.c_int64)]
+                ("status", C.c_int), ("windows", C.c_int), ("alg_bytes", C.c_int64),
+                ("phase_cycles", C.c_int64 * 6), ("slots_simulated", C.c_int64)]
 
 
 class RunArgs(C.Structure):

@@ -38,6 +38,8 @@ class ChainResult:
     total_edges: int
     windows: int
     alg_bytes: int
+    phase_cycles: tuple
+    slots_simulated: int
     final_parents: np.ndarray   # [P, max_par], -1 padded, per-child list order
     final_npar: np.ndarray
     accepted_moves: Optional[np.ndarray] = None  # rows (iter, movetype, child, parent)
@@ -259,7 +261,8 @@ class Context:
             out.append(ChainResult(
                 trace=trace, uniforms=int(s.uniforms), valid_iters=int(s.valid_iters),
                 proposed=tuple(s.proposed), reject=tuple(s.reject), n_nonpd=int(s.n_nonpd),
-                total_edges=int(s.total_edges), windows=int(s.windows), alg_bytes=int(s.alg_bytes),
+                total_edges=int(s.total_edges), windows=int(s.windows), alg_bytes=int(s.alg_bytes), phase_cycles=tuple(s.phase_cycles),
+                slots_simulated=int(s.slots_simulated),
                 final_parents=fp_ch,
                 final_npar=fnpar[ch].copy(),
                 accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])].copy(),

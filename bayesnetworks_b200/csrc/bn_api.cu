@@ -641,6 +641,8 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
       s.n_nonpd = res[ch].n_nonpd; s.total_edges = res[ch].total_edges; s.status = res[ch].status;
       s.windows = res[ch].windows;
       s.alg_bytes = res[ch].alg_bytes;
+      for (int t = 0; t < 6; t++) s.phase_cycles[t] = res[ch].cyc[t];
+      s.slots_simulated = res[ch].slots_sim;
     }
     if (res[ch].status && !rc)
       rc = fail(res[ch].status, "chain %d: no legal proposal within the uniform window (all candidate nodes are sources/full/sinks?)", ch);

@@ -73,6 +73,8 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int64_t valid_iters;
   int gll_ok; double gll;
   int64_t alg_bytes;   // sum over scored proposals of 8*(k'+1)(k'+2)/2 + 8
+  long long cyc[6];    // cycles per phase: refill, replay (A), score (B/C), commit, accepted add, accepted delete
+  long long slots_sim; // iterations replayed speculatively (committed + discarded)
   int win;             // current window size
   int windows;
   int status;
@@ -89,6 +91,14 @@ struct WindowSlots {  // shared memory on the device
   int t_rec[WIN];   // consumed | type << 8 | cyc << 9 | ovf << 10
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
+
+BN_HD long long cycle_now() {
+#if defined(__CUDA_ARCH__)
+  return clock64();
+#else
+  return 0;
+#endif
+}
 
 BN_HD bool test_bit(const uint32_t* row, int b) { return (row[b >> 5] >> (b & 31)) & 1u; }
 
@@ -363,12 +373,65 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
   Warp::sync();
   for (int i = l; i < n; i += Warp::NL) order[atomic_fetch_inc(&hist[key[i]])] = list[i];
   Warp::sync();
-  recompute_row(p, m, c, g.chunks);
+  // Change propagation: a descendant is recomputed only if one of its parents changed, and
+  // marked changed only if its own row did -- with redundant paths the wave dies out quickly.
+  uint32_t* dirty = (uint32_t*)key;  // keys are no longer needed once `order` is built
+  for (int w = l; w < p.W; w += Warp::NL) dirty[w] = 0u;
   Warp::sync();
-  for (int idx = 0; idx < n; idx++) {
-    recompute_row(p, m, order[idx], g.chunks);
-    Warp::sync();
+  recompute_row(p, m, c, g.chunks);
+  if (l == 0) dirty[c >> 5] |= 1u << (c & 31);
+  Warp::sync();
+  // 32 rows at a time: every lane checks whether one of ITS row's parents is dirty; touched
+  // rows are recomputed in order, and a row that really changed triggers a re-check of the
+  // later rows of the chunk (they may depend on it).
+  for (int i0 = 0; i0 < n; i0 += Warp::NL) {
+    const int i = i0 + l;
+    const int d_mine = (i < n) ? order[i] : -1;
+    int touched = 0;
+    if (d_mine >= 0) {
+      const int kd = m.npar[d_mine];
+      const int* pd = m.par + (int64_t)d_mine * p.max_par;
+      for (int e = 0; e < kd; e++) {
+        const int q = pd[e];
+        touched |= (dirty[q >> 5] >> (q & 31)) & 1u;
+      }
+    }
+    uint32_t mask = Warp::ballot(touched);
+    while (mask) {
+      const int b = ffs32(mask) - 1;
+      const int d = order[i0 + b];
+      const int kd = m.npar[d];
+      const int* pd = m.par + (int64_t)d * p.max_par;
+      U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
+      int changed = 0;
+      for (int ch = l; ch < g.chunks; ch += Warp::NL) {
+        U4 v = {0u, 0u, 0u, 0u};
+        for (int e = 0; e < kd; e++) {
+          const int q = pd[e];
+          v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
+          if (ch == (q >> 7)) v = with_bit(v, q & 127);
+        }
+        if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
+      }
+      const uint32_t above = (b == 31) ? 0u : ~((2u << b) - 1u);
+      if (Warp::ballot(changed) != 0u) {
+        if (l == 0) dirty[d >> 5] |= 1u << (d & 31);
+        Warp::sync();
+        // later rows of this chunk may have d as a parent
+        int t2 = touched;
+        if (d_mine >= 0 && l > b && !touched) {
+          const int kd2 = m.npar[d_mine];
+          const int* pd2 = m.par + (int64_t)d_mine * p.max_par;
+          for (int e = 0; e < kd2; e++) t2 |= (pd2[e] == d) ? 1 : 0;
+        }
+        touched = t2;
+        mask = Warp::ballot(touched) & above;
+      } else {
+        mask &= above;
+      }
+    }
   }
+  Warp::sync();
 }
 
 // full build (chain start from a non-empty graph): Jacobi sweeps to the fixpoint
@@ -458,6 +521,8 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   s.n_rows = 0; s.n_moves = 0; s.valid_iters = 0; s.alg_bytes = 0;
   s.gll_ok = 0; s.gll = 0.0;
   s.win = 4; s.windows = 0; s.status = 0;
+  for (int t = 0; t < 6; t++) s.cyc[t] = 0;
+  s.slots_sim = 0;
 }
 
 // globalLL = sum_p score(p) of the kept graph (LogLikelihood(1), src/network.h:239-247).
@@ -839,7 +904,11 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
     s.n_nonpd += popc32(m_npd);
     if (m_acc) {
       const int b = ffs32(m_acc) - 1;  // == the last committed slot
+      const long long ta = cycle_now();
       apply_move(p, m, s, s.iter + i0 + b, ws, i0 + b);
+      const long long dt = cycle_now() - ta;
+      s.cyc[ws.type[i0 + b] == 1 ? 4 : 5] += dt;
+      s.cyc[3] -= dt;
       if (m_log & m_acc)
         write_row(p, m, s, s.iter + i0 + b, ws, i0 + b, s.proposed[1] - s.reject[1],
                   s.proposed[2] - s.reject[2]);
@@ -864,7 +933,10 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   const int l = Warp::lane();
   chain_init<KMAX>(p, m, s);
   while (s.iter < p.n_iter) {
+    long long t0 = cycle_now();
     rng_top_up(rng, s.read_pos);
+    long long t1 = cycle_now();
+    s.cyc[0] += t1 - t0;
     int want = s.win;
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     int overflow = 0;
@@ -875,6 +947,9 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
       s.status = 4;  // BN_ERR_NO_LEGAL_PROPOSAL
       break;
     }
+    t0 = cycle_now();
+    s.cyc[1] += t0 - t1;
+    s.slots_sim += n;
     for (int i = l; i < n; i += Warp::NL) phase_bc<KMAX>(p, m, s, ws, i);
     Warp::sync();
     int first = -1;
@@ -883,8 +958,11 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
       const uint32_t am = Warp::ballot(i < n && ws.valid[i < n ? i : 0] && ws.accept[i < n ? i : 0]);
       if (am) first = i0 + ffs32(am) - 1;
     }
+    t1 = cycle_now();
+    s.cyc[2] += t1 - t0;
     const int ncommit = (first >= 0) ? first + 1 : n;
     commit(p, m, s, ws, ncommit);
+    s.cyc[3] += cycle_now() - t1;
     s.windows++;
     if (first >= 0) {
       int w = 2 * (first + 1);

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
     r.windows = s.windows;
     r.n_rows = s.n_rows;
     r.n_moves = s.n_moves;
+    for (int t = 0; t < 6; t++) r.cyc[t] = s.cyc[t];
+    r.slots_sim = s.slots_sim;
   }
 }
 

@@ -163,6 +163,9 @@ typedef struct bn_chain_stats {
   int windows;             /* speculative windows executed */
   int64_t alg_bytes;       /* sum over scored proposals of 8*(k'+1)(k'+2)/2 + 8: the algorithmic
                               gather bytes of the roofline (k' = parents in the scored set) */
+  int64_t phase_cycles[6]; /* SM cycles of the chain's warp per phase: uniform refill, draw replay,
+                              scoring + decision, commit, accepted additions, accepted deletions */
+  int64_t slots_simulated; /* iterations replayed speculatively (committed + discarded) */
 } bn_chain_stats;
 
 typedef struct bn_run_args {

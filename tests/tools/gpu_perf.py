@@ -30,3 +30,6 @@ for it in [iters]:
     print(f"run {chains} chains x {it}: kernel {ms:.1f} ms wall {1e3*(t1-t0):.1f} ms -> {chains*it/ms/1e3:.3f} M iters/s, "
           f"{1e3*ms/it:.3f} us/iter/chain, valid {vi/(chains*it):.3f}, iters/window {chains*it/win:.1f}, "
           f"edges {np.mean([r.total_edges for r in res]):.0f}, accepted {np.mean([sum(r.proposed)-sum(r.reject[1:]) for r in res]):.0f}", flush=True)
+    cyc = np.array([r.phase_cycles for r in res], dtype=np.float64).mean(0)
+    names = ["refill", "replayA", "scoreBC", "commit", "acc_add", "acc_del"]
+    print("cycles/iter/chain: " + ", ".join(f"{n} {c/it:.0f}" for n, c in zip(names, cyc)) + f"  total {cyc.sum()/it:.0f}; slots simulated/iter {np.mean([r.slots_simulated for r in res])/it:.2f}", flush=True)
