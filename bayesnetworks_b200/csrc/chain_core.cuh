@@ -29,6 +29,7 @@
 namespace bn {
 
 constexpr int WIN = 32;  // speculative window (iterations), one lane each
+constexpr int REPLAY_POS = 128;  // stream positions replayed per round (4 warps x 32 lanes)
 
 struct ChainParams {  // read-only, shared by all chains of a run
   int P, max_par, W, Ws, n_samples;  // W = words per bitset, Ws = row stride of anc (odd when in smem)
@@ -87,8 +88,8 @@ struct WindowSlots {  // shared memory on the device
   double u_acc[WIN], new_score[WIN];
   signed char type[WIN], valid[WIN], do_check[WIN], accept[WIN], nonpd[WIN];
   // lane-parallel draw replay: outcome of a slot that would start at stream position pos + lane
-  int t_c[WIN], t_j[WIN], t_e[WIN];
-  int t_rec[WIN];   // consumed | type << 8 | cyc << 9 | ovf << 10
+  int t_c[REPLAY_POS], t_j[REPLAY_POS], t_e[REPLAY_POS];
+  int t_rec[REPLAY_POS];   // consumed | type << 8 | cyc << 9 | ovf << 10
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
@@ -271,7 +272,7 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
 // The CTA of a chain has HELPER_WARPS extra warps parked on a named barrier; they take an
 // equal share of the rows of an ancestor update (the scan and the ORs are independent per row).
 constexpr int HELPER_WARPS = 3;
-enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1 };
+enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_REPLAY = 2 };
 BN_HD void helper_row_range(int P, int part, int nparts, int* d_lo, int* d_hi) {
   const int per = ((P + nparts - 1) / nparts + 31) / 32 * 32;
   *d_lo = part * per < P ? part * per : P;
@@ -299,22 +300,6 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
   anc_add_part(p, m, j, c, m.scratch, 0, p.P);
 }
 
-#if defined(__CUDACC__)
-// body of a helper warp (warp index 1..HELPER_WARPS of the chain's CTA)
-__device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem& m, int part) {
-  for (;;) {
-    cta_bar(1);
-    const int op = m.helper[0];
-    if (op == HELPER_EXIT) break;
-    if (op == HELPER_ANC_ADD) {
-      int lo, hi;
-      helper_row_range(p.P, part, HELPER_WARPS + 1, &lo, &hi);
-      anc_add_part(p, m, m.helper[1], m.helper[2], m.scratch + part * scratch_stride(p.P), lo, hi);
-    }
-    cta_bar(2);
-  }
-}
-#endif
 
 // after removing a parent of child c (par[c] already updated).  If the remaining parents
 // still reach everything c reached, nothing changes anywhere (the common case in a graph
@@ -624,65 +609,89 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
 // ~32/5 iterations for the latency of one.  Requires TotalEdges >= 4 so that the
 // `TotalEdges < 3` branch of src/bayesnet_mcmc.cpp:48 cannot fire inside the window.
 // ---------------------------------------------------------------------------
+// outcome of the iteration that would start at stream position q -> record slot `slot`
+BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar, const double* ubuf,
+                           int64_t hi, int64_t q, WindowSlots& ws, int slot) {
+  const int P = p.P, MP = p.max_par;
+  int64_t i = q;
+  int ovf = 0, type, c = 0, j = 0, e = -1, cyc = 0;
+  double u;
+#define BN_UAT(dst)                                    \
+  do {                                                 \
+    if (i >= hi) { ovf = 1; dst = 0.75; }              \
+    else dst = ubuf[i & (RNG_CAP - 1)];                \
+    i++;                                               \
+  } while (0)
+  BN_UAT(u);
+  if (u > 0.5) {
+    type = 1;
+    for (;;) {
+      BN_UAT(u);
+      c = (int)(P * u);
+      if (ovf || (p.node_type[c] != 1 && m.npar[c] < MP)) break;
+    }
+    const int kc = ovf ? 0 : m.npar[c];
+    const int* pc = m.par + (int64_t)c * MP;
+    for (;;) {
+      BN_UAT(u);
+      j = (int)(P * u);
+      if (ovf) break;
+      int ok = (p.node_type[j] != 2 && j != c);
+      for (int t = 0; t < kc; t++) if (pc[t] == j) ok = 0;
+      if (ok) break;
+    }
+    if (!ovf) cyc = (j == c || test_bit(m.anc + (int64_t)j * p.Ws, c)) ? 1 : 0;
+  } else {
+    type = 2;
+    BN_UAT(u);  // drawn and discarded (src/network.h:309)
+    BN_UAT(u);
+    const int idx = (int)(n_haspar * u);
+    BN_UAT(u);
+    if (!ovf) {
+      c = m.hp_list[idx];
+      e = (int)(m.npar[c] * u);
+      j = m.par[(int64_t)c * MP + e];
+    }
+  }
+#undef BN_UAT
+  ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e;
+  ws.t_rec[slot] = (int)(i - q) | ((type - 1) << 8) | (cyc << 9) | (ovf << 10);
+}
+
 BN_HD int phase_a_fast(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
                        const RngStream& rng, WindowSlots& ws, int want, int* overflow) {
-  const int P = p.P, MP = p.max_par, l = Warp::lane();
+  const int l = Warp::lane();
   const int64_t hi = rng.gen_hi;
   int64_t pos = s.read_pos;
   int v = s.valid, n = 0;
   *overflow = 0;
   bool stop = false;
   while (n < want && !stop) {
-    {
-      int64_t i = pos + l;
-      int ovf = 0, type, c = 0, j = 0, e = -1, cyc = 0;
-      double u;
-#define BN_UAT(dst)                                    \
-  do {                                                 \
-    if (i >= hi) { ovf = 1; dst = 0.75; }              \
-    else dst = rng.ubuf[i & (RNG_CAP - 1)];            \
-    i++;                                               \
-  } while (0)
-      BN_UAT(u);
-      if (u > 0.5) {
-        type = 1;
-        for (;;) {
-          BN_UAT(u);
-          c = (int)(P * u);
-          if (ovf || (p.node_type[c] != 1 && m.npar[c] < MP)) break;
-        }
-        const int kc = ovf ? 0 : m.npar[c];
-        const int* pc = m.par + (int64_t)c * MP;
-        for (;;) {
-          BN_UAT(u);
-          j = (int)(P * u);
-          if (ovf) break;
-          int ok = (p.node_type[j] != 2 && j != c);
-          for (int q = 0; q < kc; q++) if (pc[q] == j) ok = 0;
-          if (ok) break;
-        }
-        if (!ovf) cyc = (j == c || test_bit(m.anc + (int64_t)j * p.Ws, c)) ? 1 : 0;
-      } else {
-        type = 2;
-        BN_UAT(u);  // drawn and discarded (src/network.h:309)
-        BN_UAT(u);
-        const int idx = (int)(s.n_haspar * u);
-        BN_UAT(u);
-        if (!ovf) {
-          c = m.hp_list[idx];
-          e = (int)(m.npar[c] * u);
-          j = m.par[(int64_t)c * MP + e];
-        }
+    int span = Warp::NL;  // positions replayed this round
+#if defined(__CUDA_ARCH__)
+    if (m.helper) {
+      // all four warps of the CTA: 128 positions for the latency of 32
+      if (l == 0) {
+        m.helper[1] = (int)(pos & 0xffffffffll); m.helper[2] = (int)(pos >> 32);
+        m.helper[3] = (int)(hi & 0xffffffffll); m.helper[4] = (int)(hi >> 32);
+        m.helper[5] = s.n_haspar;
+        m.helper[0] = HELPER_REPLAY;
       }
-#undef BN_UAT
-      ws.t_c[l] = c; ws.t_j[l] = j; ws.t_e[l] = e;
-      ws.t_rec[l] = (int)(i - (pos + l)) | ((type - 1) << 8) | (cyc << 9) | (ovf << 10);
+      Warp::sync();
+      cta_bar(1);
+      replay_position(p, m, s.n_haspar, rng.ubuf, hi, pos + l, ws, l);
+      cta_bar(2);
+      span = REPLAY_POS;
+    } else
+#endif
+    {
+      replay_position(p, m, s.n_haspar, rng.ubuf, hi, pos + l, ws, l);
+      Warp::sync();
     }
-    Warp::sync();
     // walk: which records are real iteration starts (cheap, warp-uniform)
     int k = 0;
-    const int n0 = n, v0 = v;
-    while (n < want && k < Warp::NL) {
+    const int n0 = n;
+    while (n < want && k < span) {
       const int rec = ws.t_rec[k];
       if (rec & (1 << 10)) { *overflow = (n == 0); stop = true; break; }
       const int valid = (rec & (1 << 8)) ? v : !((rec >> 9) & 1);
@@ -695,7 +704,6 @@ BN_HD int phase_a_fast(const ChainParams& p, const ChainMem& m, const ChainScala
     }
     Warp::sync();
     // emit: one lane per new slot
-    (void)v0;
     for (int q0 = n0; q0 < n; q0 += Warp::NL) {
       const int q = q0 + l;
       if (q < n) {
@@ -717,6 +725,30 @@ BN_HD int phase_a_fast(const ChainParams& p, const ChainMem& m, const ChainScala
   }
   return n;
 }
+
+#if defined(__CUDACC__)
+// body of a helper warp (warp index 1..HELPER_WARPS of the chain's CTA)
+__device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem& m, int part,
+                                            const double* ubuf, WindowSlots& ws) {
+  for (;;) {
+    cta_bar(1);
+    const int op = m.helper[0];
+    if (op == HELPER_EXIT) break;
+    if (op == HELPER_REPLAY) {
+      const int64_t pos = ((int64_t)m.helper[2] << 32) | (uint32_t)m.helper[1];
+      const int64_t hi = ((int64_t)m.helper[4] << 32) | (uint32_t)m.helper[3];
+      const int slot = part * 32 + Warp::lane();
+      replay_position(p, m, m.helper[5], ubuf, hi, pos + slot, ws, slot);
+    }
+    if (op == HELPER_ANC_ADD) {
+      int lo, hi;
+      helper_row_range(p.P, part, HELPER_WARPS + 1, &lo, &hi);
+      anc_add_part(p, m, m.helper[1], m.helper[2], m.scratch + part * scratch_stride(p.P), lo, hi);
+    }
+    cta_bar(2);
+  }
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // Phase B + C for one slot (one lane): score the proposed set and decide.

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
                                                    ChainSmemPlan sm, ChainResult* __restrict__ results) {
   __shared__ double ubuf[RNG_CAP];
   __shared__ WindowSlots ws;
-  __shared__ int helper_cmd[4];
+  __shared__ int helper_cmd[8];
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x;
@@ -53,15 +53,15 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
 
   ChainParams pp = p;
   if (!m.moves) pp.moves_capacity = 0;
-  if (warp != 0) {  // helper warps: parked on a named barrier until the chain needs them
-    helper_loop(pp, m, warp);
-    return;
-  }
   if (sm.off_types >= 0) {
     uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);
-    for (int i = lane; i < p.P; i += 32) t[i] = p.node_type[i];
-    __syncwarp();
+    for (int i = threadIdx.x; i < p.P; i += blockDim.x) t[i] = p.node_type[i];
     pp.node_type = t;
+  }
+  __syncthreads();
+  if (warp != 0) {  // helper warps: parked on a named barrier until the chain needs them
+    helper_loop(pp, m, warp, ubuf, ws);
+    return;
   }
   ChainScalars s;
   run_chain<KMAX>(pp, m, s, rng, ws);
