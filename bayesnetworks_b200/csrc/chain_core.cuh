@@ -28,8 +28,18 @@
 
 namespace bn {
 
-constexpr int WIN = 32;  // speculative window (iterations), one lane each
-constexpr int REPLAY_POS = 128;  // stream positions replayed per round (4 warps x 32 lanes)
+constexpr int WIN = 32;  // iterations committed per epoch, one lane each
+constexpr int REPLAY_POS = 128;  // stream positions replayed and scored per round (4 warps x 32 lanes)
+
+// t_rec layout of a position record
+constexpr int REC_LEN_MASK = 0xff;      // uniforms consumed before the acceptance draw
+constexpr int REC_TYPE = 1 << 8;        // 0 = addition, 1 = deletion
+constexpr int REC_CYC = 1 << 9;         // addition that closes a cycle (invalid)
+constexpr int REC_OVF = 1 << 10;        // ran out of the uniform ring
+constexpr int REC_AG = 1 << 11;         // edge is in the prior graph
+constexpr int REC_ACC = 1 << 12;        // checker() accepts (given the iteration is valid)
+constexpr int REC_NPD = 1 << 13;        // non-positive-definite parent Gram
+constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set
 
 struct ChainParams {  // read-only, shared by all chains of a run
   int P, max_par, W, Ws, n_samples;  // W = words per bitset, Ws = row stride of anc (odd when in smem)
@@ -89,7 +99,8 @@ struct WindowSlots {  // shared memory on the device
   signed char type[WIN], valid[WIN], do_check[WIN], accept[WIN], nonpd[WIN];
   // lane-parallel draw replay: outcome of a slot that would start at stream position pos + lane
   int t_c[REPLAY_POS], t_j[REPLAY_POS], t_e[REPLAY_POS];
-  int t_rec[REPLAY_POS];   // consumed | type << 8 | cyc << 9 | ovf << 10
+  int t_rec[REPLAY_POS];   // REC_* bits
+  double t_score[REPLAY_POS];  // score of the proposed parent set
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
@@ -190,8 +201,18 @@ BN_HD int atomic_fetch_inc(int* p) {
 #endif
 }
 
-// scratch layout: four int arrays of P32 entries
-BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 32; }
+BN_HD uint32_t atomic_or_u32(uint32_t* p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return atomicOr(p, v);
+#else
+  const uint32_t o = *p; *p = o | v; return o;
+#endif
+}
+
+// scratch: 4 * scratch_stride(P) ints per chain.  anc_add_part: one list per warp at
+// part * stride.  anc_del_team: two lists of rows_per_part(P, nparts) per warp, then three
+// dirty bitsets and four round flags (2 * P + 3 * W + 300 ints at most).
+BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 64; }
 
 // nodes that have c as an ancestor (ascending), optionally preceded by c itself
 BN_HD int collect_desc_range(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list,
@@ -272,9 +293,13 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
 // The CTA of a chain has HELPER_WARPS extra warps parked on a named barrier; they take an
 // equal share of the rows of an ancestor update (the scan and the ORs are independent per row).
 constexpr int HELPER_WARPS = 3;
-enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_REPLAY = 2 };
+enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_RECORDS = 2, HELPER_REPAIR = 3, HELPER_ANC_DEL = 4 };
+// command block (ints): [0] op, [1..2] stream position, [3..4] ring limit, [5] n_haspar,
+// [6] TotalEdges, [7] Nagree, [8] node / parent, [9] child, [10] span limit (atomicMin target)
+constexpr int HELPER_WORDS = 12;
+BN_HD int rows_per_part(int P, int nparts) { return ((P + nparts - 1) / nparts + 31) / 32 * 32; }
 BN_HD void helper_row_range(int P, int part, int nparts, int* d_lo, int* d_hi) {
-  const int per = ((P + nparts - 1) / nparts + 31) / 32 * 32;
+  const int per = rows_per_part(P, nparts);
   *d_lo = part * per < P ? part * per : P;
   *d_hi = (part + 1) * per < P ? (part + 1) * per : P;
 }
@@ -283,11 +308,19 @@ __device__ __forceinline__ void cta_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"((HELPER_WARPS + 1) * 32) : "memory");
 }
 #endif
+// barrier between the rounds of a team operation (all warps of the CTA, or just this warp)
+BN_HD void team_sync(const ChainMem& m) {
+#if defined(__CUDA_ARCH__)
+  if (m.helper) { cta_bar(3); return; }
+#endif
+  (void)m;
+  Warp::sync();
+}
 
 BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
-    if (Warp::lane() == 0) { m.helper[1] = j; m.helper[2] = c; m.helper[0] = HELPER_ANC_ADD; }
+    if (Warp::lane() == 0) { m.helper[8] = j; m.helper[9] = c; m.helper[0] = HELPER_ANC_ADD; }
     Warp::sync();
     cta_bar(1);
     int lo, hi;
@@ -303,14 +336,89 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
 
 // after removing a parent of child c (par[c] already updated).  If the remaining parents
 // still reach everything c reached, nothing changes anywhere (the common case in a graph
-// with redundant paths).  Otherwise recompute c and its descendants in a topological
-// order: |anc(x)| < |anc(d)| whenever x is an ancestor of d, so a counting sort by the OLD
-// ancestor counts gives such an order.
+// with redundant paths).  Otherwise the ancestor equations anc[d] = U_q (anc[q] u {q}) over
+// the parents q of d are re-solved on desc(c): in a DAG they have ONE solution, so chaotic
+// relaxation from the old rows converges to it.  Round r recomputes the rows that have a
+// parent whose row changed in round r-1 (change propagation -- with redundant paths the wave
+// dies out quickly); the rows of a round are independent, so every warp of the CTA relaxes
+// the descendants inside its own row range.  A row read while its owner rewrites it yields a
+// mix of old and new chunks, which is harmless: the owner marks it dirty, so the reader is
+// relaxed again next round with the final value.
+BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts) {
+  const RowGeom g = row_geom(p);
+  const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr, P = p.P, W = p.W, MP = p.max_par;
+  const int per = rows_per_part(P, nparts);
+  int* list = m.scratch + part * 2 * per;
+  int* list2 = list + per;
+  uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * per);
+  volatile int* flags = (volatile int*)(dirty + 3 * W);
+  int lo, hi;
+  helper_row_range(P, part, nparts, &lo, &hi);
+  const int n = collect_desc_range(p, m, c, 0, list, lo, hi);  // old column c: rows this warp owns
+  const uint32_t lt = (l == 31) ? 0x7fffffffu : ((1u << l) - 1u);
+  for (int round = 0;; round++) {
+    const uint32_t* dprev = dirty + (round % 3) * W;
+    uint32_t* dnext = dirty + ((round + 1) % 3) * W;
+    if (part == 0) {  // nobody reads or writes these during this round
+      uint32_t* dclr = dirty + ((round + 2) % 3) * W;
+      for (int w = l; w < W; w += Warp::NL) dclr[w] = 0u;
+      if (l == 0) flags[(round + 2) % 4] = 0;
+    }
+    int nt = 0;
+    for (int i0 = 0; i0 < n; i0 += Warp::NL) {
+      const int i = i0 + l;
+      const int d = (i < n) ? list[i] : -1;
+      int touched = 0;
+      if (d >= 0) {
+        const int kd = m.npar[d];
+        const int* pd = m.par + (int64_t)d * MP;
+        for (int e = 0; e < kd; e++) {
+          const int q = pd[e];
+          touched |= (dprev[q >> 5] >> (q & 31)) & 1u;
+        }
+      }
+      const uint32_t mask = Warp::ballot(touched);
+      if (touched) list2[nt + popc32(mask & lt)] = d;
+      nt += popc32(mask);
+    }
+    Warp::sync();
+    int any = 0;
+    for (int r0 = 0; r0 < nt; r0 += g.rpp) {
+      const int r = r0 + sub;
+      int changed = 0, d = 0;
+      if (r < nt) {
+        d = list2[r];
+        const int kd = m.npar[d];
+        const int* pd = m.par + (int64_t)d * MP;
+        U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
+        for (int ch = li; ch < g.chunks; ch += g.lpr) {
+          U4 v = {0u, 0u, 0u, 0u};
+          for (int e = 0; e < kd; e++) {
+            const int q = pd[e];
+            v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
+            if (ch == (q >> 7)) v = with_bit(v, q & 127);
+          }
+          if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
+        }
+      }
+      const uint32_t mask = Warp::ballot(changed);
+      const uint32_t gm = (g.lpr >= 32 ? 0xffffffffu : ((1u << g.lpr) - 1u)) << (sub * g.lpr);
+      if (r < nt && li == 0 && (mask & gm)) atomic_or_u32(&dnext[d >> 5], 1u << (d & 31));
+      any |= (mask != 0u);
+      Warp::sync();  // later passes of this warp see the new rows
+    }
+    if (any && l == 0) flags[round % 4] = 1;
+    team_sync(m);
+    if (flags[round % 4] == 0) break;
+  }
+}
+
 BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
   const RowGeom g = row_geom(p);
-  const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr, P = p.P;
+  const int l = Warp::lane();
   {
-    const U4* ac = (const U4*)(m.anc + (int64_t)c * p.Ws);
+    // new row of c from its remaining parents; unchanged -> nothing else can change
+    U4* ac = (U4*)(m.anc + (int64_t)c * p.Ws);
     const int* pc = m.par + (int64_t)c * p.max_par;
     const int kc = m.npar[c];
     int changed = 0;
@@ -321,102 +429,32 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
         v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
         if (ch == (q >> 7)) v = with_bit(v, q & 127);
       }
-      if (ne4(v, ac[ch])) changed = 1;
+      if (ne4(v, ac[ch])) { ac[ch] = v; changed = 1; }
     }
     if (Warp::ballot(changed) == 0u) return;
   }
-  const int st = scratch_stride(P);
-  int* list = m.scratch;
-  int* key = m.scratch + st;
-  int* hist = m.scratch + 2 * st;
-  int* order = m.scratch + 3 * st;
-  const int n = collect_desc(p, m, c, 0, list);  // proper descendants, old ancestor sets
-  for (int r0 = 0; r0 < n; r0 += g.rpp) {
-    const int r = r0 + sub;
-    int cnt = 0;
-    if (r < n) {
-      const U4* ad = (const U4*)(m.anc + (int64_t)list[r] * p.Ws);
-      for (int ch = li; ch < g.chunks; ch += g.lpr) cnt += popc4(ad[ch]);
-    }
-    cnt = group_sum(cnt, g.lpr);
-    if (r < n && li == 0) key[r] = cnt;
-  }
-  for (int i = l; i <= P; i += Warp::NL) hist[i] = 0;
-  Warp::sync();
-  for (int i = l; i < n; i += Warp::NL) atomic_fetch_inc(&hist[key[i]]);
-  Warp::sync();
+  int nparts = 1;
+#if defined(__CUDA_ARCH__)
+  if (m.helper) nparts = HELPER_WARPS + 1;
+#endif
   {
-    const int per = (P + 1 + Warp::NL - 1) / Warp::NL;
-    const int lo = l * per;
-    int hi = lo + per;
-    if (hi > P + 1) hi = P + 1;
-    int local = 0;
-    for (int i = lo; i < hi; i++) local += hist[i];
-    int run = Warp::incl_scan(local) - local;
-    for (int i = lo; i < hi; i++) { const int t = hist[i]; hist[i] = run; run += t; }
+    uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * rows_per_part(p.P, nparts));
+    for (int w = l; w < 3 * p.W + 4; w += Warp::NL) dirty[w] = 0u;  // three bitsets + four flags
+    Warp::sync();
+    if (l == 0) dirty[c >> 5] = 1u << (c & 31);
+    Warp::sync();
   }
-  Warp::sync();
-  for (int i = l; i < n; i += Warp::NL) order[atomic_fetch_inc(&hist[key[i]])] = list[i];
-  Warp::sync();
-  // Change propagation: a descendant is recomputed only if one of its parents changed, and
-  // marked changed only if its own row did -- with redundant paths the wave dies out quickly.
-  uint32_t* dirty = (uint32_t*)key;  // keys are no longer needed once `order` is built
-  for (int w = l; w < p.W; w += Warp::NL) dirty[w] = 0u;
-  Warp::sync();
-  recompute_row(p, m, c, g.chunks);
-  if (l == 0) dirty[c >> 5] |= 1u << (c & 31);
-  Warp::sync();
-  // 32 rows at a time: every lane checks whether one of ITS row's parents is dirty; touched
-  // rows are recomputed in order, and a row that really changed triggers a re-check of the
-  // later rows of the chunk (they may depend on it).
-  for (int i0 = 0; i0 < n; i0 += Warp::NL) {
-    const int i = i0 + l;
-    const int d_mine = (i < n) ? order[i] : -1;
-    int touched = 0;
-    if (d_mine >= 0) {
-      const int kd = m.npar[d_mine];
-      const int* pd = m.par + (int64_t)d_mine * p.max_par;
-      for (int e = 0; e < kd; e++) {
-        const int q = pd[e];
-        touched |= (dirty[q >> 5] >> (q & 31)) & 1u;
-      }
-    }
-    uint32_t mask = Warp::ballot(touched);
-    while (mask) {
-      const int b = ffs32(mask) - 1;
-      const int d = order[i0 + b];
-      const int kd = m.npar[d];
-      const int* pd = m.par + (int64_t)d * p.max_par;
-      U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
-      int changed = 0;
-      for (int ch = l; ch < g.chunks; ch += Warp::NL) {
-        U4 v = {0u, 0u, 0u, 0u};
-        for (int e = 0; e < kd; e++) {
-          const int q = pd[e];
-          v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
-          if (ch == (q >> 7)) v = with_bit(v, q & 127);
-        }
-        if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
-      }
-      const uint32_t above = (b == 31) ? 0u : ~((2u << b) - 1u);
-      if (Warp::ballot(changed) != 0u) {
-        if (l == 0) dirty[d >> 5] |= 1u << (d & 31);
-        Warp::sync();
-        // later rows of this chunk may have d as a parent
-        int t2 = touched;
-        if (d_mine >= 0 && l > b && !touched) {
-          const int kd2 = m.npar[d_mine];
-          const int* pd2 = m.par + (int64_t)d_mine * p.max_par;
-          for (int e = 0; e < kd2; e++) t2 |= (pd2[e] == d) ? 1 : 0;
-        }
-        touched = t2;
-        mask = Warp::ballot(touched) & above;
-      } else {
-        mask &= above;
-      }
-    }
+#if defined(__CUDA_ARCH__)
+  if (m.helper) {
+    if (l == 0) { m.helper[9] = c; m.helper[0] = HELPER_ANC_DEL; }
+    Warp::sync();
+    cta_bar(1);
+    anc_del_team(p, m, c, 0, nparts);
+    cta_bar(2);
+    return;
   }
-  Warp::sync();
+#endif
+  anc_del_team(p, m, c, 0, 1);
 }
 
 // full build (chain start from a non-empty graph): Jacobi sweeps to the fixpoint
@@ -601,15 +639,111 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
 }
 
 // ---------------------------------------------------------------------------
-// Phase A, lane-parallel.  The only sequential dependence between iterations is the stream
-// position (each iteration consumes a data-dependent number of uniforms) and the stale
-// `valid` flag.  So lane l replays the iteration that WOULD start at position pos + l
-// (move type, rejection-sampled child/parent, cycle test, uniforms consumed); a short
-// pointer walk then picks the records that are real iteration starts.  One round yields
-// ~32/5 iterations for the latency of one.  Requires TotalEdges >= 4 so that the
-// `TotalEdges < 3` branch of src/bayesnet_mcmc.cpp:48 cannot fire inside the window.
+// Score of the parent set a proposal would leave at child c (push_back / erase order,
+// src/network.h:303,325).
 // ---------------------------------------------------------------------------
-// outcome of the iteration that would start at stream position q -> record slot `slot`
+template <int KMAX>
+BN_HD double score_proposal(const ChainParams& p, const ChainMem& m, int type, int c, int j, int del,
+                            int* kk_out, int* npd) {
+  const int* pc = m.par + (int64_t)c * p.max_par;
+  const int k = m.npar[c];
+  int kk = 0;
+  double nw;
+  if constexpr (KMAX <= 8) {
+    int S[KMAX];
+    if (type == 1) {
+      kk = k + 1;
+#pragma unroll
+      for (int e = 0; e < KMAX; e++) S[e] = (e < k) ? pc[e] : j;
+    } else {
+      kk = k - 1;
+#pragma unroll
+      for (int e = 0; e < KMAX; e++) {
+        const int src = e + (e >= del ? 1 : 0);
+        S[e] = (src < k) ? pc[src] : c;
+      }
+    }
+    nw = score_set_small<KMAX>(p.C, p.ldc, c, S, kk, p.n_samples, npd);
+  } else {
+    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
+    int S[KMAX];
+    if (type == 1) {
+      for (int e = 0; e < k; e++) S[kk++] = pc[e];
+      S[kk++] = j;
+    } else {
+      for (int e = 0; e < k; e++) if (e != del) S[kk++] = pc[e];
+    }
+    nw = score_set(p.C, p.ldc, c, S, kk, p.n_samples, L, z, npd);
+  }
+  *kk_out = kk;
+  return nw;
+}
+
+// ---------------------------------------------------------------------------
+// Phase B + C for one slot (one lane): score the proposed set and decide.
+// ---------------------------------------------------------------------------
+template <int KMAX>
+BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
+                    WindowSlots& ws, int i) {
+  const int c = ws.child[i], j = ws.parent[i];
+  const int fp_true = s.te_true - s.agree_true, fn_true = p.n_sim_edges - s.agree_true;
+  if (!ws.valid[i]) {
+    // invalid: only OldLogPrior ran, the members describe the current graph
+    ws.fp_m[i] = fp_true; ws.fn_m[i] = fn_true;
+    ws.accept[i] = 0; ws.nonpd[i] = 0; ws.kk[i] = 0;
+    return;
+  }
+  {
+    const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
+    const int ag_new = s.agree_true + (ws.type[i] == 1 ? ag : -ag);
+    ws.fp_m[i] = ws.te_m[i] - ag_new;
+    ws.fn_m[i] = p.n_sim_edges - ag_new;
+  }
+  int kk = 0, npd = 0;
+  const double nw = score_proposal<KMAX>(p, m, ws.type[i], c, j, ws.pos[i], &kk, &npd);
+  ws.new_score[i] = nw;
+  ws.kk[i] = kk;
+  ws.nonpd[i] = (signed char)npd;
+  // HR = exp(NewLogLike - OldLogLike + NewLogPrior - OldLogPrior), src/network.h:334
+  const double old_prior = prior_value(p.phi, p.omega, fp_true + fn_true, s.te_true);
+  const double new_prior = prior_value(p.phi, p.omega, ws.fp_m[i] + ws.fn_m[i], ws.te_m[i]);
+  const double arg = sub_rn(add_rn(sub_rn(nw, m.base[c]), new_prior), old_prior);
+  const double HR = exp(arg);
+  ws.accept[i] = (ws.u_acc[i] > HR) ? 0 : 1;  // reject iff runif > HR (NaN accepts), :335
+}
+
+// ---------------------------------------------------------------------------
+// Rounds: position-parallel speculation.
+//
+// The only sequential dependences between iterations are the stream position (each
+// iteration consumes a data-dependent number of uniforms), the stale `valid` flag, and the
+// graph itself, which changes on the ~5% of iterations that are accepted.  So one thread
+// per stream position q in [pos, pos + REPLAY_POS) builds the RECORD of the iteration that
+// WOULD start at q: draw replay (move type, rejection-sampled child/parent, uniforms
+// consumed, cycle test), the score of the proposed parent set, and the accept decision.
+// Roughly one position in five is a real iteration start; the rest is latency-free slack
+// of the four warps.  The chain's own warp then walks the records from the committed
+// position (pointer chase over `consumed`), commits rejected iterations in bulk, and on an
+// accepted move applies it and REPAIRS the remaining records instead of discarding them:
+//   * a record depends on the graph only through its child's parent list (replay of the
+//     duplicate test / deletion index, score, base score), the ancestor bit of its
+//     (parent, child) pair, and the global counts TotalEdges / Nagree (prior terms);
+//   * records of the changed child are stale: the walk stops in front of the first one
+//     and the next round starts there;
+//   * cycle bits are re-tested and the accept decisions re-evaluated with the new prior
+//     terms by all threads (cyclic additions are scored too, so a bit that clears after a
+//     deletion needs no new score);
+//   * a move that changes the set of nodes with parents (deletion draws index into it) or
+//     moves the child across the MaxPar limit (child rejection loop) ends the round.
+// Requires TotalEdges >= 4 so that the `TotalEdges < 3` branch of
+// src/bayesnet_mcmc.cpp:48 cannot fire; the sequential window path covers the rest.
+// ---------------------------------------------------------------------------
+struct RoundCtx {  // warp-uniform, handed to the helper warps through the command block
+  int64_t pos, hi;
+  int n_haspar, te_true, agree_true;
+};
+
+// draw replay of the iteration that would start at stream position q -> record `slot`
 BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar, const double* ubuf,
                            int64_t hi, int64_t q, WindowSlots& ws, int slot) {
   const int P = p.P, MP = p.max_par;
@@ -622,8 +756,9 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
     else dst = ubuf[i & (RNG_CAP - 1)];                \
     i++;                                               \
   } while (0)
-  BN_UAT(u);
+  BN_UAT(u);  // u_move, src/bayesnet_mcmc.cpp:48
   if (u > 0.5) {
+    // propose_addition, src/network.h:281-306
     type = 1;
     for (;;) {
       BN_UAT(u);
@@ -640,10 +775,12 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
       for (int t = 0; t < kc; t++) if (pc[t] == j) ok = 0;
       if (ok) break;
     }
-    if (!ovf) cyc = (j == c || test_bit(m.anc + (int64_t)j * p.Ws, c)) ? 1 : 0;
+    // CheckValidity -> pathExists (src/network.h:366-432): is c an ancestor of j?
+    if (!ovf) cyc = test_bit(m.anc + (int64_t)j * p.Ws, c) ? 1 : 0;
   } else {
+    // propose_deletion, src/network.h:308-328
     type = 2;
-    BN_UAT(u);  // drawn and discarded (src/network.h:309)
+    BN_UAT(u);  // drawn and discarded (:309)
     BN_UAT(u);
     const int idx = (int)(n_haspar * u);
     BN_UAT(u);
@@ -654,164 +791,202 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
     }
   }
 #undef BN_UAT
+  if (i >= hi) ovf = 1;  // the acceptance uniform must be in the ring as well
   ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e;
-  ws.t_rec[slot] = (int)(i - q) | ((type - 1) << 8) | (cyc << 9) | (ovf << 10);
+  ws.t_rec[slot] = (int)(i - q) | (type == 2 ? REC_TYPE : 0) | (cyc ? REC_CYC : 0) | (ovf ? REC_OVF : 0);
 }
 
-BN_HD int phase_a_fast(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
-                       const RngStream& rng, WindowSlots& ws, int want, int* overflow) {
-  const int l = Warp::lane();
-  const int64_t hi = rng.gen_hi;
-  int64_t pos = s.read_pos;
-  int v = s.valid, n = 0;
-  *overflow = 0;
-  bool stop = false;
-  while (n < want && !stop) {
-    int span = Warp::NL;  // positions replayed this round
-#if defined(__CUDA_ARCH__)
-    if (m.helper) {
-      // all four warps of the CTA: 128 positions for the latency of 32
-      if (l == 0) {
-        m.helper[1] = (int)(pos & 0xffffffffll); m.helper[2] = (int)(pos >> 32);
-        m.helper[3] = (int)(hi & 0xffffffffll); m.helper[4] = (int)(hi >> 32);
-        m.helper[5] = s.n_haspar;
-        m.helper[0] = HELPER_REPLAY;
-      }
-      Warp::sync();
-      cta_bar(1);
-      replay_position(p, m, s.n_haspar, rng.ubuf, hi, pos + l, ws, l);
-      cta_bar(2);
-      span = REPLAY_POS;
-    } else
-#endif
-    {
-      replay_position(p, m, s.n_haspar, rng.ubuf, hi, pos + l, ws, l);
-      Warp::sync();
-    }
-    // walk: which records are real iteration starts (cheap, warp-uniform)
-    int k = 0;
-    const int n0 = n;
-    while (n < want && k < span) {
-      const int rec = ws.t_rec[k];
-      if (rec & (1 << 10)) { *overflow = (n == 0); stop = true; break; }
-      const int valid = (rec & (1 << 8)) ? v : !((rec >> 9) & 1);
-      const int len = (rec & 0xff) + (valid ? 1 : 0);
-      if (pos + k + len > hi) { *overflow = (n == 0); stop = true; break; }
-      if (l == 0) ws.s_k[n] = k | (valid << 16);
-      v = valid;
-      k += len;
-      n++;
-    }
-    Warp::sync();
-    // emit: one lane per new slot
-    for (int q0 = n0; q0 < n; q0 += Warp::NL) {
-      const int q = q0 + l;
-      if (q < n) {
-        const int sk = ws.s_k[q];
-        const int kk = sk & 0xffff, valid = sk >> 16;
-        const int rec = ws.t_rec[kk];
-        const int type = ((rec >> 8) & 1) + 1;
-        const int cons = rec & 0xff;
-        const int64_t at = pos + kk + cons;
-        ws.child[q] = ws.t_c[kk]; ws.parent[q] = ws.t_j[kk]; ws.pos[q] = ws.t_e[kk];
-        ws.type[q] = (signed char)type; ws.valid[q] = (signed char)valid;
-        ws.te_m[q] = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
-        ws.u_acc[q] = valid ? rng.ubuf[at & (RNG_CAP - 1)] : 0.0;
-        ws.pos_after[q] = at + (valid ? 1 : 0);
-      }
-    }
-    pos += k;
-    Warp::sync();
+// checker() for a record under the current global counts: sets REC_AG / REC_ACC
+BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                         WindowSlots& ws, int slot) {
+  int rec = ws.t_rec[slot];
+  if (rec & REC_OVF) return;
+  const int c = ws.t_c[slot], j = ws.t_j[slot];
+  const int type = (rec & REC_TYPE) ? 2 : 1;
+  const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
+  const int te_new = rc.te_true + (type == 1 ? 1 : -1);
+  const int ag_new = rc.agree_true + (type == 1 ? ag : -ag);
+  const int fp_true = rc.te_true - rc.agree_true, fn_true = p.n_sim_edges - rc.agree_true;
+  const double old_prior = prior_value(p.phi, p.omega, fp_true + fn_true, rc.te_true);
+  const double new_prior = prior_value(p.phi, p.omega, (te_new - ag_new) + (p.n_sim_edges - ag_new), te_new);
+  // HR = exp(NewLogLike - OldLogLike + NewLogPrior - OldLogPrior), src/network.h:334
+  const double arg = sub_rn(add_rn(sub_rn(ws.t_score[slot], m.base[c]), new_prior), old_prior);
+  const double HR = exp(arg);
+  const double u_acc = ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)];
+  rec &= ~(REC_AG | REC_ACC);
+  if (ag) rec |= REC_AG;
+  if (!(u_acc > HR)) rec |= REC_ACC;  // reject iff runif > HR (NaN accepts), :335
+  ws.t_rec[slot] = rec;
+}
+
+template <int KMAX>
+BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                        WindowSlots& ws, int slot) {
+  replay_position(p, m, rc.n_haspar, ubuf, rc.hi, rc.pos + slot, ws, slot);
+  const int rec = ws.t_rec[slot];
+  if (rec & REC_OVF) return;
+  int kk = 0, npd = 0;
+  ws.t_score[slot] = score_proposal<KMAX>(p, m, (rec & REC_TYPE) ? 2 : 1, ws.t_c[slot], ws.t_j[slot],
+                                          ws.t_e[slot], &kk, &npd);
+  ws.t_rec[slot] = rec | (npd ? REC_NPD : 0) | (kk << REC_KK_SHIFT);
+  decide_record(p, m, rc, ubuf, ws, slot);
+}
+
+// after an accepted move at child c: stale records bound the walk, cycle bits and accept
+// decisions are refreshed
+// returns the slot when its record is stale, REPLAY_POS otherwise
+BN_HD int repair_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                        WindowSlots& ws, int slot, int c, int from) {
+  if (slot < from) return REPLAY_POS;
+  int rec = ws.t_rec[slot];
+  if (rec & REC_OVF) return REPLAY_POS;
+  if (ws.t_c[slot] == c) return slot;
+  if (!(rec & REC_TYPE)) {
+    const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, ws.t_c[slot]) ? 1 : 0;
+    rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
+    ws.t_rec[slot] = rec;
   }
-  return n;
+  decide_record(p, m, rc, ubuf, ws, slot);
+  return REPLAY_POS;
 }
 
 #if defined(__CUDACC__)
+__device__ __forceinline__ void helper_post(const ChainMem& m, int op, const RoundCtx& rc) {
+  if (Warp::lane() == 0) {
+    m.helper[1] = (int)(rc.pos & 0xffffffffll); m.helper[2] = (int)(rc.pos >> 32);
+    m.helper[3] = (int)(rc.hi & 0xffffffffll); m.helper[4] = (int)(rc.hi >> 32);
+    m.helper[5] = rc.n_haspar; m.helper[6] = rc.te_true; m.helper[7] = rc.agree_true;
+    m.helper[0] = op;
+  }
+  Warp::sync();
+}
+__device__ __forceinline__ RoundCtx helper_ctx(const ChainMem& m) {
+  RoundCtx rc;
+  rc.pos = ((int64_t)m.helper[2] << 32) | (uint32_t)m.helper[1];
+  rc.hi = ((int64_t)m.helper[4] << 32) | (uint32_t)m.helper[3];
+  rc.n_haspar = m.helper[5]; rc.te_true = m.helper[6]; rc.agree_true = m.helper[7];
+  return rc;
+}
+
 // body of a helper warp (warp index 1..HELPER_WARPS of the chain's CTA)
+template <int KMAX>
 __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem& m, int part,
                                             const double* ubuf, WindowSlots& ws) {
   for (;;) {
     cta_bar(1);
     const int op = m.helper[0];
     if (op == HELPER_EXIT) break;
-    if (op == HELPER_REPLAY) {
-      const int64_t pos = ((int64_t)m.helper[2] << 32) | (uint32_t)m.helper[1];
-      const int64_t hi = ((int64_t)m.helper[4] << 32) | (uint32_t)m.helper[3];
-      const int slot = part * 32 + Warp::lane();
-      replay_position(p, m, m.helper[5], ubuf, hi, pos + slot, ws, slot);
-    }
-    if (op == HELPER_ANC_ADD) {
+    const int slot = part * 32 + Warp::lane();
+    if (op == HELPER_RECORDS) {
+      build_record<KMAX>(p, m, helper_ctx(m), ubuf, ws, slot);
+    } else if (op == HELPER_REPAIR) {
+      const int stale = repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[8]);
+      if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
+    } else if (op == HELPER_ANC_ADD) {
       int lo, hi;
       helper_row_range(p.P, part, HELPER_WARPS + 1, &lo, &hi);
-      anc_add_part(p, m, m.helper[1], m.helper[2], m.scratch + part * scratch_stride(p.P), lo, hi);
+      anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * scratch_stride(p.P), lo, hi);
+    } else if (op == HELPER_ANC_DEL) {
+      anc_del_team(p, m, m.helper[9], part, HELPER_WARPS + 1);
     }
     cta_bar(2);
   }
 }
 #endif
 
-// ---------------------------------------------------------------------------
-// Phase B + C for one slot (one lane): score the proposed set and decide.
-// ---------------------------------------------------------------------------
 template <int KMAX>
-BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
-                    WindowSlots& ws, int i) {
-  const int c = ws.child[i], j = ws.parent[i], MP = p.max_par;
-  const int fp_true = s.te_true - s.agree_true, fn_true = p.n_sim_edges - s.agree_true;
-  if (!ws.valid[i]) {
-    // invalid: only OldLogPrior ran, the members describe the current graph
-    ws.fp_m[i] = fp_true; ws.fn_m[i] = fn_true;
-    ws.accept[i] = 0; ws.nonpd[i] = 0; ws.kk[i] = 0;
+BN_HD void team_records(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                        WindowSlots& ws) {
+#if defined(__CUDA_ARCH__)
+  if (m.helper) {
+    helper_post(m, HELPER_RECORDS, rc);
+    cta_bar(1);
+    build_record<KMAX>(p, m, rc, ubuf, ws, Warp::lane());
+    cta_bar(2);
     return;
   }
-  {
-    const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
-    const int ag_new = s.agree_true + (ws.type[i] == 1 ? ag : -ag);
-    ws.fp_m[i] = ws.te_m[i] - ag_new;
-    ws.fn_m[i] = p.n_sim_edges - ag_new;
+#endif
+  for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL) build_record<KMAX>(p, m, rc, ubuf, ws, slot);
+  Warp::sync();
+}
+
+// returns the new span limit
+BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                      WindowSlots& ws, int c, int from, int span_limit) {
+#if defined(__CUDA_ARCH__)
+  if (m.helper) {
+    if (Warp::lane() == 0) { m.helper[8] = from; m.helper[9] = c; m.helper[10] = span_limit; }
+    helper_post(m, HELPER_REPAIR, rc);
+    cta_bar(1);
+    const int stale = repair_record(p, m, rc, ubuf, ws, Warp::lane(), c, from);
+    if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
+    cta_bar(2);
+    return m.helper[10];
   }
-  const int* pc = m.par + (int64_t)c * MP;
-  const int k = m.npar[c];
-  int kk = 0;
-  int npd = 0;
-  double nw;
-  if constexpr (KMAX <= 8) {
-    int S[KMAX];
-    if (ws.type[i] == 1) {
-      kk = k + 1;  // push_back, src/network.h:303
-#pragma unroll
-      for (int e = 0; e < KMAX; e++) S[e] = (e < k) ? pc[e] : j;
-    } else {
-      const int del = ws.pos[i];
-      kk = k - 1;  // erase keeps the order, :325
-#pragma unroll
-      for (int e = 0; e < KMAX; e++) {
-        const int src = e + (e >= del ? 1 : 0);
-        S[e] = (src < k) ? pc[src] : c;
+#endif
+  int lim = span_limit;
+  for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL) {
+    const int stale = repair_record(p, m, rc, ubuf, ws, slot, c, from);
+    lim = stale < lim ? stale : lim;
+  }
+  Warp::sync();
+  return Warp::min(lim);
+}
+
+// Walk the records from relative position *k: emits up to `want` slots, stops behind the
+// first accepted one.  Returns the number of slots; *ovf when the walk hit an overflowed
+// record.
+BN_HD int walk_emit(const ChainParams& p, const ChainScalars& s, const RngStream& rng, WindowSlots& ws,
+                    int64_t round_pos, int* k_io, int span_limit, int want, int* ovf) {
+  const int l = Warp::lane();
+  int k = *k_io, v = s.valid, n = 0;
+  *ovf = 0;
+  while (n < want && k < span_limit) {
+    const int rec = ws.t_rec[k];
+    if (rec & REC_OVF) { *ovf = 1; break; }
+    // `valid` is only assigned by additions (src/bayesnet_mcmc.cpp:50-52)
+    const int valid = (rec & REC_TYPE) ? v : !(rec & REC_CYC);
+    if (l == 0) ws.s_k[n] = k | (valid << 16);
+    v = valid;
+    k += (rec & REC_LEN_MASK) + valid;  // the acceptance uniform is drawn for valid iterations only
+    n++;
+    if (valid && (rec & REC_ACC)) break;
+  }
+  Warp::sync();
+  const int fp_true = s.te_true - s.agree_true, fn_true = p.n_sim_edges - s.agree_true;
+  for (int q0 = 0; q0 < n; q0 += Warp::NL) {
+    const int q = q0 + l;
+    if (q < n) {
+      const int sk = ws.s_k[q];
+      const int kk = sk & 0xffff, valid = sk >> 16;
+      const int rec = ws.t_rec[kk];
+      const int type = (rec & REC_TYPE) ? 2 : 1;
+      const int64_t at = round_pos + kk + (rec & REC_LEN_MASK);
+      ws.child[q] = ws.t_c[kk]; ws.parent[q] = ws.t_j[kk]; ws.pos[q] = ws.t_e[kk];
+      ws.type[q] = (signed char)type; ws.valid[q] = (signed char)valid;
+      const int te_m = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
+      ws.te_m[q] = te_m;
+      ws.u_acc[q] = valid ? rng.ubuf[at & (RNG_CAP - 1)] : 0.0;
+      ws.pos_after[q] = at + (valid ? 1 : 0);
+      if (valid) {
+        // members left by checker()'s LogPrior() on the proposed graph, src/network.h:333
+        const int ag = (rec & REC_AG) ? 1 : 0;
+        const int ag_new = s.agree_true + (type == 1 ? ag : -ag);
+        ws.fp_m[q] = te_m - ag_new; ws.fn_m[q] = p.n_sim_edges - ag_new;
+        ws.new_score[q] = ws.t_score[kk];
+        ws.kk[q] = rec >> REC_KK_SHIFT;
+        ws.nonpd[q] = (rec & REC_NPD) ? 1 : 0;
+        ws.accept[q] = (rec & REC_ACC) ? 1 : 0;
+      } else {
+        // invalid: only OldLogPrior ran, the members describe the current graph
+        ws.fp_m[q] = fp_true; ws.fn_m[q] = fn_true;
+        ws.new_score[q] = 0.0; ws.kk[q] = 0; ws.nonpd[q] = 0; ws.accept[q] = 0;
       }
     }
-    nw = score_set_small<KMAX>(p.C, p.ldc, c, S, kk, p.n_samples, &npd);
-  } else {
-    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
-    int S[KMAX];
-    if (ws.type[i] == 1) {
-      for (int e = 0; e < k; e++) S[kk++] = pc[e];
-      S[kk++] = j;
-    } else {
-      const int del = ws.pos[i];
-      for (int e = 0; e < k; e++) if (e != del) S[kk++] = pc[e];
-    }
-    nw = score_set(p.C, p.ldc, c, S, kk, p.n_samples, L, z, &npd);
   }
-  ws.new_score[i] = nw;
-  ws.kk[i] = kk;
-  ws.nonpd[i] = (signed char)npd;
-  // HR = exp(NewLogLike - OldLogLike + NewLogPrior - OldLogPrior), src/network.h:334
-  const double old_prior = prior_value(p.phi, p.omega, fp_true + fn_true, s.te_true);
-  const double new_prior = prior_value(p.phi, p.omega, ws.fp_m[i] + ws.fn_m[i], ws.te_m[i]);
-  const double arg = sub_rn(add_rn(sub_rn(nw, m.base[c]), new_prior), old_prior);
-  const double HR = exp(arg);
-  ws.accept[i] = (ws.u_acc[i] > HR) ? 0 : 1;  // reject iff runif > HR (NaN accepts), :335
+  Warp::sync();
+  *k_io = k;
+  return n;
 }
 
 // ---------------------------------------------------------------------------
@@ -959,22 +1134,78 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
 // ---------------------------------------------------------------------------
 // The whole chain.
 // ---------------------------------------------------------------------------
+// One round: records for REPLAY_POS positions, then walk / commit / repair epochs.
+template <int KMAX>
+BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng, WindowSlots& ws) {
+  long long t0 = cycle_now();
+  RoundCtx rc;
+  rc.pos = s.read_pos; rc.hi = rng.gen_hi;
+  rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+  team_records<KMAX>(p, m, rc, rng.ubuf, ws);
+  long long t1 = cycle_now();
+  s.cyc[1] += t1 - t0;
+  int k = 0, span_limit = REPLAY_POS;
+  for (;;) {
+    t0 = cycle_now();
+    int want = WIN;
+    if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
+    if (want <= 0) break;
+    int ovf = 0;
+    const int k0 = k;
+    const int n = walk_emit(p, s, rng, ws, rc.pos, &k, span_limit, want, &ovf);
+    t1 = cycle_now();
+    s.cyc[2] += t1 - t0;
+    if (n == 0) {
+      if (ovf && k0 == 0) s.status = 4;  // BN_ERR_NO_LEGAL_PROPOSAL: one iteration outran the ring
+      break;
+    }
+    s.slots_sim += n;
+    const int last = n - 1;
+    const int accepted = ws.valid[last] && ws.accept[last];
+    const int c = ws.child[last], type = ws.type[last], nh0 = s.n_haspar;
+    commit(p, m, s, ws, n);
+    s.cyc[3] += cycle_now() - t1;
+    if (ovf || k >= span_limit) break;
+    if (accepted) {
+      // moves that invalidate every record: the set of nodes with parents changed (deletion
+      // draws), c crossed the MaxPar limit (child rejection loop), TotalEdges < 4
+      const int kc = m.npar[c];
+      if (s.n_haspar != nh0 || s.te_true < 4 || (type == 1 && kc == p.max_par) ||
+          (type == 2 && kc == p.max_par - 1))
+        break;
+      t0 = cycle_now();
+      rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+      span_limit = team_repair(p, m, rc, rng.ubuf, ws, c, k, span_limit);
+      s.cyc[2] += cycle_now() - t0;
+      if (k >= span_limit) break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The whole chain.
+// ---------------------------------------------------------------------------
 template <int KMAX>
 BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
                      WindowSlots& ws) {
   const int l = Warp::lane();
   chain_init<KMAX>(p, m, s);
-  while (s.iter < p.n_iter) {
+  while (s.iter < p.n_iter && s.status == 0) {
     long long t0 = cycle_now();
     rng_top_up(rng, s.read_pos);
     long long t1 = cycle_now();
     s.cyc[0] += t1 - t0;
+    s.windows++;
+    // position-parallel rounds need `TotalEdges < 3` to be impossible
+    if (s.te_true >= 4 && s.te_m >= 3) {
+      run_round<KMAX>(p, m, s, rng, ws);
+      continue;
+    }
+    // sequential windows (first iterations of a chain, tiny graphs)
     int want = s.win;
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     int overflow = 0;
-    // the lane-parallel replay needs `TotalEdges < 3` to be impossible inside the window
-    const int n = (s.te_true >= 4 && s.te_m >= 3) ? phase_a_fast(p, m, s, rng, ws, want, &overflow)
-                                                  : phase_a(p, m, s, rng, ws, want, &overflow);
+    const int n = phase_a(p, m, s, rng, ws, want, &overflow);
     if (n == 0) {
       s.status = 4;  // BN_ERR_NO_LEGAL_PROPOSAL
       break;
@@ -995,7 +1226,6 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     const int ncommit = (first >= 0) ? first + 1 : n;
     commit(p, m, s, ws, ncommit);
     s.cyc[3] += cycle_now() - t1;
-    s.windows++;
     if (first >= 0) {
       int w = 2 * (first + 1);
       s.win = w < 2 ? 2 : (w > WIN ? WIN : w);

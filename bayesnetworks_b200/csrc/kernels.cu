@@ -17,7 +17,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
                                                    ChainSmemPlan sm, ChainResult* __restrict__ results) {
   __shared__ double ubuf[RNG_CAP];
   __shared__ WindowSlots ws;
-  __shared__ int helper_cmd[8];
+  __shared__ int helper_cmd[HELPER_WORDS];
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
   }
   __syncthreads();
   if (warp != 0) {  // helper warps: parked on a named barrier until the chain needs them
-    helper_loop(pp, m, warp, ubuf, ws);
+    helper_loop<KMAX>(pp, m, warp, ubuf, ws);
     return;
   }
   ChainScalars s;
