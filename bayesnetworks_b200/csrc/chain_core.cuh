@@ -39,6 +39,7 @@ constexpr int REC_OVF = 1 << 10;        // ran out of the uniform ring
 constexpr int REC_AG = 1 << 11;         // edge is in the prior graph
 constexpr int REC_ACC = 1 << 12;        // checker() accepts (given the iteration is valid)
 constexpr int REC_NPD = 1 << 13;        // non-positive-definite parent Gram
+constexpr int REC_FULLMANY = 1 << 14;   // more than two children were skipped for being at MaxPar
 constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set
 
 struct ChainParams {  // read-only, shared by all chains of a run
@@ -88,6 +89,7 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   long long slots_sim; // iterations replayed speculatively (committed + discarded)
   int win;             // current window size
   int windows;
+  int need_full;       // the last round could not start: top the ring up completely before retrying
   int status;
 };
 
@@ -101,6 +103,7 @@ struct WindowSlots {  // shared memory on the device
   int t_c[REPLAY_POS], t_j[REPLAY_POS], t_e[REPLAY_POS];
   int t_rec[REPLAY_POS];   // REC_* bits
   double t_score[REPLAY_POS];  // score of the proposed parent set
+  uint32_t t_full[REPLAY_POS]; // the (up to two) children the draw skipped for being at MaxPar, +1, 16 bits each
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
@@ -214,27 +217,34 @@ BN_HD uint32_t atomic_or_u32(uint32_t* p, uint32_t v) {
 // dirty bitsets and four round flags (2 * P + 3 * W + 300 ints at most).
 BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 64; }
 
-// nodes that have c as an ancestor (ascending), optionally preceded by c itself
-BN_HD int collect_desc_range(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list,
-                             int d_lo, int d_hi) {
+// nodes that have c as an ancestor (ascending), optionally c itself as well: the share of
+// `part` under a block-cyclic partition of the rows (blocks of Warp::NL rows; descendants
+// cluster in index ranges, contiguous ranges would leave most of the work to one warp)
+BN_HD int collect_desc_part(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list,
+                            int part, int nparts) {
   const int l = Warp::lane();
   const uint32_t Ws = (uint32_t)p.Ws, cb = (uint32_t)c & 31u;
   const uint32_t* col = m.anc + (c >> 5);  // word (c >> 5) of every row
   const uint32_t lt = (1u << l) - 1u;
   int n = 0;
-  for (int d0 = d_lo; d0 < d_hi; d0 += Warp::NL) {
-    const int d = d0 + l;
-    int flag = 0;
-    if (d < d_hi) flag = ((col[(uint32_t)d * Ws] >> cb) & 1u) | ((include_self && d == c) ? 1 : 0);
-    const uint32_t mask = Warp::ballot(flag);
-    if (flag) list[n + popc32(mask & lt)] = d;
-    n += popc32(mask);
+  const int step = nparts * Warp::NL;
+  for (int d0 = part * Warp::NL; d0 < p.P; d0 += 4 * step) {  // four independent column loads in flight
+    int d[4], flag[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      d[t] = d0 + t * step + l;
+      flag[t] = 0;
+      if (d[t] < p.P) flag[t] = ((col[(uint32_t)d[t] * Ws] >> cb) & 1u) | ((include_self && d[t] == c) ? 1 : 0);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const uint32_t mask = Warp::ballot(flag[t]);
+      if (flag[t]) list[n + popc32(mask & lt)] = d[t];
+      n += popc32(mask);
+    }
   }
   Warp::sync();
   return n;
-}
-BN_HD int collect_desc(const ChainParams& p, const ChainMem& m, int c, int include_self, int* list) {
-  return collect_desc_range(p, m, c, include_self, list, 0, p.P);
 }
 
 // anc[d] = union over the parents q of d of (anc[q] u {q}); all lanes, one row
@@ -254,11 +264,11 @@ BN_HD void recompute_row(const ChainParams& p, ChainMem& m, int d, int chunks) {
 }
 
 // after adding parent j to child c: every node in {c} u desc(c) gains anc[j] u {j}
-// rows [d_lo, d_hi) of the update: one warp's share (the whole range on the host)
-BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, int* list, int d_lo, int d_hi) {
+// (one warp's share of the rows; everything on the host)
+BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, int* list, int part, int nparts) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr;
-  const int n = collect_desc_range(p, m, c, 1, list, d_lo, d_hi);
+  const int n = collect_desc_part(p, m, c, 1, list, part, nparts);
   const U4* aj = (const U4*)(m.anc + (uint32_t)j * (uint32_t)p.Ws);
   if (g.chunks <= g.lpr) {
     // one 128-bit chunk per lane (up to 4,096 nodes): the source chunk stays in registers
@@ -267,12 +277,18 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
       a = aj[li];
       if (li == (j >> 7)) a = with_bit(a, j & 127);
     }
-    for (int r0 = 0; r0 < n; r0 += g.rpp) {
-      const int r = r0 + sub;
-      if (r < n && li < g.chunks) {
-        U4* ad = (U4*)(m.anc + (uint32_t)list[r] * (uint32_t)p.Ws) + li;
-        *ad = or4(*ad, a);
+    for (int r0 = 0; r0 < n; r0 += 4 * g.rpp) {  // four rows in flight per lane group
+      U4* ad[4];
+      U4 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int r = r0 + t * g.rpp + sub;
+        ad[t] = (r < n && li < g.chunks) ? (U4*)(m.anc + (uint32_t)list[r] * (uint32_t)p.Ws) + li : nullptr;
       }
+#pragma unroll
+      for (int t = 0; t < 4; t++) if (ad[t]) v[t] = *ad[t];
+#pragma unroll
+      for (int t = 0; t < 4; t++) if (ad[t]) *ad[t] = or4(v[t], a);
     }
   } else {
     for (int r0 = 0; r0 < n; r0 += g.rpp) {
@@ -293,15 +309,15 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
 // The CTA of a chain has HELPER_WARPS extra warps parked on a named barrier; they take an
 // equal share of the rows of an ancestor update (the scan and the ORs are independent per row).
 constexpr int HELPER_WARPS = 3;
-enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_RECORDS = 2, HELPER_REPAIR = 3, HELPER_ANC_DEL = 4 };
+enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_RECORDS = 2, HELPER_REPAIR = 3, HELPER_ANC_DEL = 4,
+       HELPER_FILL_WH = 5 };
 // command block (ints): [0] op, [1..2] stream position, [3..4] ring limit, [5] n_haspar,
-// [6] TotalEdges, [7] Nagree, [8] node / parent, [9] child, [10] span limit (atomicMin target)
+// [6] TotalEdges, [7] Nagree, [8] node / parent, [9] child, [10] span limit (atomicMin target),
+// [11] child dropped below MaxPar
 constexpr int HELPER_WORDS = 12;
-BN_HD int rows_per_part(int P, int nparts) { return ((P + nparts - 1) / nparts + 31) / 32 * 32; }
-BN_HD void helper_row_range(int P, int part, int nparts, int* d_lo, int* d_hi) {
-  const int per = rows_per_part(P, nparts);
-  *d_lo = part * per < P ? part * per : P;
-  *d_hi = (part + 1) * per < P ? (part + 1) * per : P;
+BN_HD int rows_per_part(int P, int nparts) {  // most rows one warp can own (block-cyclic)
+  const int nblk = (P + Warp::NL - 1) / Warp::NL;
+  return (nblk + nparts - 1) / nparts * Warp::NL;
 }
 #if defined(__CUDACC__)
 __device__ __forceinline__ void cta_bar(int id) {
@@ -323,16 +339,30 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
     if (Warp::lane() == 0) { m.helper[8] = j; m.helper[9] = c; m.helper[0] = HELPER_ANC_ADD; }
     Warp::sync();
     cta_bar(1);
-    int lo, hi;
-    helper_row_range(p.P, 0, HELPER_WARPS + 1, &lo, &hi);
-    anc_add_part(p, m, j, c, m.scratch, lo, hi);
+    anc_add_part(p, m, j, c, m.scratch, 0, HELPER_WARPS + 1);
     cta_bar(2);
     return;
   }
 #endif
-  anc_add_part(p, m, j, c, m.scratch, 0, p.P);
+  anc_add_part(p, m, j, c, m.scratch, 0, 1);
 }
 
+
+// parents of node d as eight slots (-1 = empty); two 128-bit loads when MaxPar == 8
+struct Par8 { int q[8]; };
+BN_HD Par8 load_par8(const ChainParams& p, const ChainMem& m, int d) {
+  Par8 r;
+  const int* pd = m.par + (int64_t)d * p.max_par;
+  if (p.max_par == 8) {
+    const U4 a = ((const U4*)pd)[0], b = ((const U4*)pd)[1];
+    r.q[0] = (int)a.x; r.q[1] = (int)a.y; r.q[2] = (int)a.z; r.q[3] = (int)a.w;
+    r.q[4] = (int)b.x; r.q[5] = (int)b.y; r.q[6] = (int)b.z; r.q[7] = (int)b.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; e++) r.q[e] = (e < p.max_par) ? pd[e] : -1;
+  }
+  return r;
+}
 
 // after removing a parent of child c (par[c] already updated).  If the remaining parents
 // still reach everything c reached, nothing changes anywhere (the common case in a graph
@@ -352,9 +382,7 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
   int* list2 = list + per;
   uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * per);
   volatile int* flags = (volatile int*)(dirty + 3 * W);
-  int lo, hi;
-  helper_row_range(P, part, nparts, &lo, &hi);
-  const int n = collect_desc_range(p, m, c, 0, list, lo, hi);  // old column c: rows this warp owns
+  const int n = collect_desc_part(p, m, c, 0, list, part, nparts);  // old column c: rows this warp owns
   const uint32_t lt = (l == 31) ? 0x7fffffffu : ((1u << l) - 1u);
   for (int round = 0;; round++) {
     const uint32_t* dprev = dirty + (round % 3) * W;
@@ -370,11 +398,19 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
       const int d = (i < n) ? list[i] : -1;
       int touched = 0;
       if (d >= 0) {
-        const int kd = m.npar[d];
-        const int* pd = m.par + (int64_t)d * MP;
-        for (int e = 0; e < kd; e++) {
-          const int q = pd[e];
-          touched |= (dprev[q >> 5] >> (q & 31)) & 1u;
+        if (MP <= 8) {
+          // unused slots of a parent list hold -1: all eight dirty words load independently
+          const Par8 pq = load_par8(p, m, d);
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (pq.q[e] >= 0) touched |= (dprev[pq.q[e] >> 5] >> (pq.q[e] & 31)) & 1u;
+        } else {
+          const int kd = m.npar[d];
+          const int* pd = m.par + (int64_t)d * MP;
+          for (int e = 0; e < kd; e++) {
+            const int q = pd[e];
+            touched |= (dprev[q >> 5] >> (q & 31)) & 1u;
+          }
         }
       }
       const uint32_t mask = Warp::ballot(touched);
@@ -388,17 +424,33 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
       int changed = 0, d = 0;
       if (r < nt) {
         d = list2[r];
-        const int kd = m.npar[d];
-        const int* pd = m.par + (int64_t)d * MP;
         U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
-        for (int ch = li; ch < g.chunks; ch += g.lpr) {
-          U4 v = {0u, 0u, 0u, 0u};
-          for (int e = 0; e < kd; e++) {
-            const int q = pd[e];
-            v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
-            if (ch == (q >> 7)) v = with_bit(v, q & 127);
+        if (MP <= 8) {
+          const Par8 pq = load_par8(p, m, d);
+          for (int ch = li; ch < g.chunks; ch += g.lpr) {
+            U4 v = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const int q = pq.q[e];
+              if (q >= 0) {
+                v = or4(v, ((const U4*)(m.anc + (uint32_t)q * (uint32_t)p.Ws))[ch]);
+                if (ch == (q >> 7)) v = with_bit(v, q & 127);
+              }
+            }
+            if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
           }
-          if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
+        } else {
+          const int kd = m.npar[d];
+          const int* pd = m.par + (int64_t)d * MP;
+          for (int ch = li; ch < g.chunks; ch += g.lpr) {
+            U4 v = {0u, 0u, 0u, 0u};
+            for (int e = 0; e < kd; e++) {
+              const int q = pd[e];
+              v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
+              if (ch == (q >> 7)) v = with_bit(v, q & 127);
+            }
+            if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
+          }
         }
       }
       const uint32_t mask = Warp::ballot(changed);
@@ -493,7 +545,8 @@ template <int KMAX>
 BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   const int l = Warp::lane(), P = p.P, MP = p.max_par;
   for (int64_t i = l; i < (int64_t)P * MP; i += Warp::NL) {
-    m.par[i] = (p.initial_network == 0) ? p.prior_par[i] : -1;
+    // unused slots hold -1 (load_par8 relies on it)
+    m.par[i] = (p.initial_network == 0 && (int)(i % MP) < p.prior_npar[i / MP]) ? p.prior_par[i] : -1;
     m.born[i] = p.drop;  // edges of the start graph are counted from iteration `drop`
   }
   for (int i = l; i < P; i += Warp::NL) m.npar[i] = (p.initial_network == 0) ? p.prior_npar[i] : 0;
@@ -543,7 +596,7 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   for (int t = 0; t < 3; t++) { s.proposed[t] = 0; s.reject[t] = 0; }
   s.n_rows = 0; s.n_moves = 0; s.valid_iters = 0; s.alg_bytes = 0;
   s.gll_ok = 0; s.gll = 0.0;
-  s.win = 4; s.windows = 0; s.status = 0;
+  s.win = 4; s.windows = 0; s.status = 0; s.need_full = 0;
   for (int t = 0; t < 6; t++) s.cyc[t] = 0;
   s.slots_sim = 0;
 }
@@ -748,7 +801,8 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
                            int64_t hi, int64_t q, WindowSlots& ws, int slot) {
   const int P = p.P, MP = p.max_par;
   int64_t i = q;
-  int ovf = 0, type, c = 0, j = 0, e = -1, cyc = 0;
+  int ovf = 0, type, c = 0, j = 0, e = -1, cyc = 0, many = 0;
+  uint32_t full = 0u;
   double u;
 #define BN_UAT(dst)                                    \
   do {                                                 \
@@ -763,7 +817,11 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
     for (;;) {
       BN_UAT(u);
       c = (int)(P * u);
-      if (ovf || (p.node_type[c] != 1 && m.npar[c] < MP)) break;
+      if (ovf || p.node_type[c] == 1) { if (ovf) break; continue; }
+      if (m.npar[c] < MP) break;
+      // skipped for being full: the record goes stale if this node loses a parent
+      if (P > 0xfffe || (full >> 16)) many = 1;
+      else full = (full << 16) | (uint32_t)(c + 1);
     }
     const int kc = ovf ? 0 : m.npar[c];
     const int* pc = m.par + (int64_t)c * MP;
@@ -792,8 +850,10 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
   }
 #undef BN_UAT
   if (i >= hi) ovf = 1;  // the acceptance uniform must be in the ring as well
-  ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e;
-  ws.t_rec[slot] = (int)(i - q) | (type == 2 ? REC_TYPE : 0) | (cyc ? REC_CYC : 0) | (ovf ? REC_OVF : 0);
+  const int ag = (!ovf && p.sim_edge[(int64_t)j + (int64_t)c * P]) ? 1 : 0;
+  ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e; ws.t_full[slot] = full;
+  ws.t_rec[slot] = (int)(i - q) | (type == 2 ? REC_TYPE : 0) | (cyc ? REC_CYC : 0) | (ovf ? REC_OVF : 0) |
+                   (ag ? REC_AG : 0) | (many ? REC_FULLMANY : 0);
 }
 
 // checker() for a record under the current global counts: sets REC_AG / REC_ACC
@@ -801,9 +861,9 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
                          WindowSlots& ws, int slot) {
   int rec = ws.t_rec[slot];
   if (rec & REC_OVF) return;
-  const int c = ws.t_c[slot], j = ws.t_j[slot];
+  const int c = ws.t_c[slot];
   const int type = (rec & REC_TYPE) ? 2 : 1;
-  const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
+  const int ag = (rec & REC_AG) ? 1 : 0;
   const int te_new = rc.te_true + (type == 1 ? 1 : -1);
   const int ag_new = rc.agree_true + (type == 1 ? ag : -ag);
   const int fp_true = rc.te_true - rc.agree_true, fn_true = p.n_sim_edges - rc.agree_true;
@@ -813,8 +873,7 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   const double arg = sub_rn(add_rn(sub_rn(ws.t_score[slot], m.base[c]), new_prior), old_prior);
   const double HR = exp(arg);
   const double u_acc = ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)];
-  rec &= ~(REC_AG | REC_ACC);
-  if (ag) rec |= REC_AG;
+  rec &= ~REC_ACC;
   if (!(u_acc > HR)) rec |= REC_ACC;  // reject iff runif > HR (NaN accepts), :335
   ws.t_rec[slot] = rec;
 }
@@ -835,13 +894,18 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
 // after an accepted move at child c: stale records bound the walk, cycle bits and accept
 // decisions are refreshed
 // returns the slot when its record is stale, REPLAY_POS otherwise
+// `unfull`: the move took c from MaxPar to MaxPar - 1 parents, so draws that skipped c differ
 BN_HD int repair_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
-                        WindowSlots& ws, int slot, int c, int from) {
+                        WindowSlots& ws, int slot, int c, int unfull, int from) {
   if (slot < from) return REPLAY_POS;
   int rec = ws.t_rec[slot];
   if (rec & REC_OVF) return REPLAY_POS;
   if (ws.t_c[slot] == c) return slot;
   if (!(rec & REC_TYPE)) {
+    if (unfull) {
+      const uint32_t f = ws.t_full[slot], cc = (uint32_t)(c + 1);
+      if ((rec & REC_FULLMANY) || (f & 0xffffu) == cc || (f >> 16) == cc) return slot;
+    }
     const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, ws.t_c[slot]) ? 1 : 0;
     rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
     ws.t_rec[slot] = rec;
@@ -868,10 +932,49 @@ __device__ __forceinline__ RoundCtx helper_ctx(const ChainMem& m) {
   return rc;
 }
 
+// Wichmann-Hill by the whole CTA: thread t jumps ahead t + 1 steps from the state in the
+// command block ([5..7]) and writes the uniform at stream position [1..2] + t; the last
+// thread leaves the new state in [8..10].
+struct WhJump { uint32_t mx, my, mz; };
+__device__ __forceinline__ WhJump wh_jump_for_thread() {
+  WhJump j;
+  j.mx = pow_mod(171u, (int)threadIdx.x + 1, 30269u);
+  j.my = pow_mod(172u, (int)threadIdx.x + 1, 30307u);
+  j.mz = pow_mod(170u, (int)threadIdx.x + 1, 30323u);
+  return j;
+}
+__device__ __forceinline__ void fill_wh_thread(const ChainMem& m, double* ubuf, const WhJump& j) {
+  const int64_t pos = ((int64_t)m.helper[2] << 32) | (uint32_t)m.helper[1];
+  const uint32_t xs = ((uint32_t)m.helper[5] * j.mx) % 30269u;
+  const uint32_t ys = ((uint32_t)m.helper[6] * j.my) % 30307u;
+  const uint32_t zs = ((uint32_t)m.helper[7] * j.mz) % 30323u;
+  ubuf[(pos + threadIdx.x) & (RNG_CAP - 1)] = wh_combine(xs, ys, zs);
+  if (threadIdx.x == (HELPER_WARPS + 1) * 32 - 1) { m.helper[8] = (int)xs; m.helper[9] = (int)ys; m.helper[10] = (int)zs; }
+}
+// chain warp: append (HELPER_WARPS + 1) * 32 uniforms while they fit in the ring
+__device__ __forceinline__ void team_fill_wh(const ChainMem& m, RngStream& r, int64_t read_pos, const WhJump& j) {
+  constexpr int TEAM = (HELPER_WARPS + 1) * 32;
+  while (r.gen_hi + TEAM <= read_pos + RNG_CAP) {
+    if (Warp::lane() == 0) {
+      m.helper[1] = (int)(r.gen_hi & 0xffffffffll); m.helper[2] = (int)(r.gen_hi >> 32);
+      m.helper[5] = (int)r.x; m.helper[6] = (int)r.y; m.helper[7] = (int)r.z;
+      m.helper[0] = HELPER_FILL_WH;
+    }
+    Warp::sync();
+    cta_bar(1);
+    fill_wh_thread(m, r.ubuf, j);
+    cta_bar(2);
+    r.x = (uint32_t)m.helper[8]; r.y = (uint32_t)m.helper[9]; r.z = (uint32_t)m.helper[10];
+    r.gen_hi += TEAM;
+    Warp::sync();
+  }
+}
+
 // body of a helper warp (warp index 1..HELPER_WARPS of the chain's CTA)
 template <int KMAX>
 __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem& m, int part,
-                                            const double* ubuf, WindowSlots& ws) {
+                                            double* ubuf, WindowSlots& ws) {
+  const WhJump jump = wh_jump_for_thread();
   for (;;) {
     cta_bar(1);
     const int op = m.helper[0];
@@ -880,14 +983,14 @@ __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem
     if (op == HELPER_RECORDS) {
       build_record<KMAX>(p, m, helper_ctx(m), ubuf, ws, slot);
     } else if (op == HELPER_REPAIR) {
-      const int stale = repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[8]);
+      const int stale = repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[11], m.helper[8]);
       if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
     } else if (op == HELPER_ANC_ADD) {
-      int lo, hi;
-      helper_row_range(p.P, part, HELPER_WARPS + 1, &lo, &hi);
-      anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * scratch_stride(p.P), lo, hi);
+      anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * scratch_stride(p.P), part, HELPER_WARPS + 1);
     } else if (op == HELPER_ANC_DEL) {
       anc_del_team(p, m, m.helper[9], part, HELPER_WARPS + 1);
+    } else if (op == HELPER_FILL_WH) {
+      fill_wh_thread(m, ubuf, jump);
     }
     cta_bar(2);
   }
@@ -912,13 +1015,13 @@ BN_HD void team_records(const ChainParams& p, const ChainMem& m, const RoundCtx&
 
 // returns the new span limit
 BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
-                      WindowSlots& ws, int c, int from, int span_limit) {
+                      WindowSlots& ws, int c, int unfull, int from, int span_limit) {
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
-    if (Warp::lane() == 0) { m.helper[8] = from; m.helper[9] = c; m.helper[10] = span_limit; }
+    if (Warp::lane() == 0) { m.helper[8] = from; m.helper[9] = c; m.helper[10] = span_limit; m.helper[11] = unfull; }
     helper_post(m, HELPER_REPAIR, rc);
     cta_bar(1);
-    const int stale = repair_record(p, m, rc, ubuf, ws, Warp::lane(), c, from);
+    const int stale = repair_record(p, m, rc, ubuf, ws, Warp::lane(), c, unfull, from);
     if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
     cta_bar(2);
     return m.helper[10];
@@ -926,7 +1029,7 @@ BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& r
 #endif
   int lim = span_limit;
   for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL) {
-    const int stale = repair_record(p, m, rc, ubuf, ws, slot, c, from);
+    const int stale = repair_record(p, m, rc, ubuf, ws, slot, c, unfull, from);
     lim = stale < lim ? stale : lim;
   }
   Warp::sync();
@@ -1090,7 +1193,7 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
     const uint32_t m_r2 = Warp::ballot(counted && type == 2 && !acc);
     const uint32_t m_npd = Warp::ballot(valid && ws.nonpd[in ? i : 0]);
     const uint32_t m_acc = Warp::ballot(acc);
-    const uint32_t m_log = Warp::ballot(valid && (it % p.output_every == 0));  // :63-65
+    const uint32_t m_log = Warp::ballot(valid && ((int)it % p.output_every == 0));  // :63-65 (n_iter is an int)
     const int kk = valid ? ws.kk[i] : 0;
     const int bytes = Warp::sum(valid ? 4 * (kk + 1) * (kk + 2) + 8 : 0);
     // rows of rejected iterations (pre-move graph), in order
@@ -1156,9 +1259,11 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     t1 = cycle_now();
     s.cyc[2] += t1 - t0;
     if (n == 0) {
-      if (ovf && k0 == 0) s.status = 4;  // BN_ERR_NO_LEGAL_PROPOSAL: one iteration outran the ring
+      // one iteration outran the uniforms in the ring: retry with a full ring, then give up
+      if (ovf && k0 == 0) { if (s.need_full) s.status = 4; else s.need_full = 1; }
       break;
     }
+    s.need_full = 0;
     s.slots_sim += n;
     const int last = n - 1;
     const int accepted = ws.valid[last] && ws.accept[last];
@@ -1168,14 +1273,13 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     if (ovf || k >= span_limit) break;
     if (accepted) {
       // moves that invalidate every record: the set of nodes with parents changed (deletion
-      // draws), c crossed the MaxPar limit (child rejection loop), TotalEdges < 4
-      const int kc = m.npar[c];
-      if (s.n_haspar != nh0 || s.te_true < 4 || (type == 1 && kc == p.max_par) ||
-          (type == 2 && kc == p.max_par - 1))
-        break;
+      // draws index into it), TotalEdges < 4.  A child that reaches MaxPar only affects its own
+      // records; one that drops below it affects the draws that skipped it.
+      if (s.n_haspar != nh0 || s.te_true < 4) break;
+      const int unfull = (type == 2 && m.npar[c] == p.max_par - 1) ? 1 : 0;
       t0 = cycle_now();
       rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
-      span_limit = team_repair(p, m, rc, rng.ubuf, ws, c, k, span_limit);
+      span_limit = team_repair(p, m, rc, rng.ubuf, ws, c, unfull, k, span_limit);
       s.cyc[2] += cycle_now() - t0;
       if (k >= span_limit) break;
     }
@@ -1190,9 +1294,19 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
                      WindowSlots& ws) {
   const int l = Warp::lane();
   chain_init<KMAX>(p, m, s);
+#if defined(__CUDA_ARCH__)
+  const WhJump jump = wh_jump_for_thread();
+#endif
   while (s.iter < p.n_iter && s.status == 0) {
     long long t0 = cycle_now();
-    rng_top_up(rng, s.read_pos);
+#if defined(__CUDA_ARCH__)
+    if (rng.kind == RNG_WH && m.helper) {
+      // the CTA appends 128 uniforms at a time (>= 385 ahead of the read position afterwards)
+      team_fill_wh(m, rng, s.read_pos, jump);
+      if (s.need_full) rng_top_up(rng, s.read_pos);
+    } else
+#endif
+      rng_top_up(rng, s.read_pos);
     long long t1 = cycle_now();
     s.cyc[0] += t1 - t0;
     s.windows++;
@@ -1207,9 +1321,11 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     int overflow = 0;
     const int n = phase_a(p, m, s, rng, ws, want, &overflow);
     if (n == 0) {
-      s.status = 4;  // BN_ERR_NO_LEGAL_PROPOSAL
-      break;
+      if (s.need_full) { s.status = 4; break; }  // BN_ERR_NO_LEGAL_PROPOSAL
+      s.need_full = 1;
+      continue;
     }
+    s.need_full = 0;
     t0 = cycle_now();
     s.cyc[1] += t0 - t1;
     s.slots_sim += n;

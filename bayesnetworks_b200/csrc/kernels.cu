@@ -12,7 +12,10 @@ namespace bn {
 // Per-chain state lives in global memory and is served from this SM's L1 (only
 // this CTA touches it); the Gram is read with L2-only loads.
 // ---------------------------------------------------------------------------
-template <int KMAX>
+// ALL_SMEM: every per-chain array of the plan sits in dynamic shared memory, so the pointers
+// have a provable shared-memory provenance and the state accesses compile to LDS/STS
+// instead of generic loads.
+template <int KMAX, bool ALL_SMEM>
 __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
                                                    ChainSmemPlan sm, ChainResult* __restrict__ results) {
   __shared__ double ubuf[RNG_CAP];
@@ -26,14 +29,24 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
   ChainMem m;
   int* g_par = w.par + ch * P * MP;
   int* g_npar = w.npar + ch * P;
-  m.par = sm.off_par >= 0 ? (int*)(dyn_smem + sm.off_par) : g_par;
-  m.npar = sm.off_npar >= 0 ? (int*)(dyn_smem + sm.off_npar) : g_npar;
   m.born = w.born + ch * P * MP;
-  m.base = sm.off_base >= 0 ? (double*)(dyn_smem + sm.off_base) : w.base + ch * P;
-  m.anc = sm.off_anc >= 0 ? (uint32_t*)(dyn_smem + sm.off_anc) : w.anc + ch * P * (int64_t)p.Ws;
-  m.haspar = sm.off_haspar >= 0 ? (uint32_t*)(dyn_smem + sm.off_haspar) : w.haspar + ch * W;
-  m.hp_list = sm.off_hplist >= 0 ? (int*)(dyn_smem + sm.off_hplist) : w.hp_list + ch * P;
-  m.scratch = sm.off_scratch >= 0 ? (int*)(dyn_smem + sm.off_scratch) : w.scratch + (int64_t)ch * w.scratch_n;
+  if constexpr (ALL_SMEM) {
+    m.par = (int*)(dyn_smem + sm.off_par);
+    m.npar = (int*)(dyn_smem + sm.off_npar);
+    m.base = (double*)(dyn_smem + sm.off_base);
+    m.anc = (uint32_t*)(dyn_smem + sm.off_anc);
+    m.haspar = (uint32_t*)(dyn_smem + sm.off_haspar);
+    m.hp_list = (int*)(dyn_smem + sm.off_hplist);
+    m.scratch = (int*)(dyn_smem + sm.off_scratch);
+  } else {
+    m.par = sm.off_par >= 0 ? (int*)(dyn_smem + sm.off_par) : g_par;
+    m.npar = sm.off_npar >= 0 ? (int*)(dyn_smem + sm.off_npar) : g_npar;
+    m.base = sm.off_base >= 0 ? (double*)(dyn_smem + sm.off_base) : w.base + ch * P;
+    m.anc = sm.off_anc >= 0 ? (uint32_t*)(dyn_smem + sm.off_anc) : w.anc + ch * P * (int64_t)p.Ws;
+    m.haspar = sm.off_haspar >= 0 ? (uint32_t*)(dyn_smem + sm.off_haspar) : w.haspar + ch * W;
+    m.hp_list = sm.off_hplist >= 0 ? (int*)(dyn_smem + sm.off_hplist) : w.hp_list + ch * P;
+    m.scratch = sm.off_scratch >= 0 ? (int*)(dyn_smem + sm.off_scratch) : w.scratch + (int64_t)ch * w.scratch_n;
+  }
   const int64_t cap = p.trace_capacity;
   m.t_iter = w.t_iter + ch * cap; m.t_changed = w.t_changed + ch * cap;
   m.t_movetype = w.t_movetype + ch * cap; m.t_gll = w.t_gll + ch * cap;
@@ -53,7 +66,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
 
   ChainParams pp = p;
   if (!m.moves) pp.moves_capacity = 0;
-  if (sm.off_types >= 0) {
+  if (ALL_SMEM || sm.off_types >= 0) {
     uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);
     for (int i = threadIdx.x; i < p.P; i += blockDim.x) t[i] = p.node_type[i];
     pp.node_type = t;
@@ -70,9 +83,9 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainPar
   cta_bar(1);
 
   // final graph back to global memory when it lived in shared memory
-  if (m.par != g_par)
+  if (ALL_SMEM || sm.off_par >= 0)
     for (int64_t i = lane; i < P * MP; i += 32) g_par[i] = m.par[i];
-  if (m.npar != g_npar)
+  if (ALL_SMEM || sm.off_npar >= 0)
     for (int64_t i = lane; i < P; i += 32) g_npar[i] = m.npar[i];
 
   if (lane == 0) {
@@ -127,16 +140,18 @@ template <int KMAX>
 static const char* launch_chains_t(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
                                    ChainResult* d_results, int n_chains, cudaStream_t stream) {
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, chain_kernel<KMAX>) != cudaSuccess) return "cudaFuncGetAttributes failed";
+  if (cudaFuncGetAttributes(&fa, chain_kernel<KMAX, true>) != cudaSuccess) return "cudaFuncGetAttributes failed";
   int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int budget = max_optin - (int)fa.sharedSizeBytes - 1024;
   ChainSmemPlan sm = plan_chain_smem(p, w.scratch_n, budget > 0 ? budget : 0);
-  if (cudaFuncSetAttribute(chain_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           sm.total_bytes) != cudaSuccess)
+  const bool all_smem = sm.off_types >= 0 && sm.off_npar >= 0 && sm.off_base >= 0 && sm.off_haspar >= 0 &&
+                        sm.off_hplist >= 0 && sm.off_par >= 0 && sm.off_scratch >= 0 && sm.off_anc >= 0;
+  auto kernel = all_smem ? chain_kernel<KMAX, true> : chain_kernel<KMAX, false>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total_bytes) != cudaSuccess)
     return "cudaFuncSetAttribute(chain_kernel) failed";
-  chain_kernel<KMAX><<<n_chains, (HELPER_WARPS + 1) * 32, sm.total_bytes, stream>>>(p, w, ra, sm, d_results);
+  kernel<<<n_chains, (HELPER_WARPS + 1) * 32, sm.total_bytes, stream>>>(p, w, ra, sm, d_results);
   return nullptr;
 }
 

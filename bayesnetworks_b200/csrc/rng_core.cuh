@@ -71,6 +71,13 @@ BN_HD void rng_init_replay(RngStream& r, const double* u, int64_t n, double* ubu
   r.x = r.y = r.z = r.mx = r.my = r.mz = 0; r.mt = nullptr; r.mti = 0;
 }
 
+// r = ix/30269.0 + iy/30307.0 + iz/30323.0; return r - floor(r)  (random4f.h:36-40)
+BN_HD double wh_combine(uint32_t xs, uint32_t ys, uint32_t zs) {
+  const double v = add_rn(add_rn(div_rn((double)xs, 30269.0), div_rn((double)ys, 30307.0)),
+                          div_rn((double)zs, 30323.0));
+  return sub_rn(v, floor(v));
+}
+
 // MT19937 state regeneration by the whole warp.
 BN_HD void rmt_twist(uint32_t* mt) {
   const int l = Warp::lane();
@@ -100,10 +107,7 @@ BN_HD int rng_fill_chunk(RngStream& r) {
     const uint32_t xs = (r.x * r.mx) % 30269u;
     const uint32_t ys = (r.y * r.my) % 30307u;
     const uint32_t zs = (r.z * r.mz) % 30323u;
-    double v = add_rn(add_rn(div_rn((double)xs, 30269.0), div_rn((double)ys, 30307.0)),
-                      div_rn((double)zs, 30323.0));
-    v = sub_rn(v, floor(v));
-    r.ubuf[(r.gen_hi + l) & (RNG_CAP - 1)] = v;
+    r.ubuf[(r.gen_hi + l) & (RNG_CAP - 1)] = wh_combine(xs, ys, zs);
     r.x = (uint32_t)Warp::shfl((int)xs, Warp::NL - 1);
     r.y = (uint32_t)Warp::shfl((int)ys, Warp::NL - 1);
     r.z = (uint32_t)Warp::shfl((int)zs, Warp::NL - 1);
