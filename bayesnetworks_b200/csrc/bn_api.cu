@@ -525,7 +525,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   DevBuf buf;
   ChainWorkspace w;
   memset(&w, 0, sizeof(w));
-  w.scratch_n = 4 * scratch_stride((int)P);
+  w.scratch_n = scratch_words((int)P, HELPER_WARPS + 1, 32);
   CU_TRY(buf.alloc(&w.par, (size_t)(nc * P * MP)));
   CU_TRY(buf.alloc(&w.born, (size_t)(nc * P * MP)));
   CU_TRY(buf.alloc(&w.npar, (size_t)(nc * P)));

@@ -29,7 +29,7 @@
 namespace bn {
 
 constexpr int WIN = 32;  // iterations committed per epoch, one lane each
-constexpr int REPLAY_POS = 128;  // stream positions replayed and scored per round (4 warps x 32 lanes)
+constexpr int REPLAY_POS = 256;  // stream positions replayed and scored per round (8 warps x 32 lanes)
 
 // t_rec layout of a position record
 constexpr int REC_LEN_MASK = 0xff;      // uniforms consumed before the acceptance draw
@@ -65,7 +65,7 @@ struct ChainMem {  // per-chain global memory
   uint32_t* anc;       // [P][Ws] ancestor bitsets
   uint32_t* haspar;    // [W] nodes with >= 1 parent (bitset)
   int* hp_list;        // [P] the same set as an ascending list (CurrOutputs, src/network.h:311-316)
-  int* scratch;        // [4 * scratch_stride(P)] lists / keys / histogram for the ancestor updates
+  int* scratch;        // [scratch_words(P, ...)] row lists / dirty bitsets of the ancestor updates
   volatile int* helper;  // device only: command block of the CTA's helper warps (null = none)
   // outputs
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
@@ -212,10 +212,16 @@ BN_HD uint32_t atomic_or_u32(uint32_t* p, uint32_t v) {
 #endif
 }
 
-// scratch: 4 * scratch_stride(P) ints per chain.  anc_add_part: one list per warp at
-// part * stride.  anc_del_team: two lists of rows_per_part(P, nparts) per warp, then three
-// dirty bitsets and four round flags (2 * P + 3 * W + 300 ints at most).
-BN_HD int scratch_stride(int P) { return ((P + 32) / 32) * 32 + 64; }
+// most rows one warp can own under the block-cyclic partition (blocks of nl rows)
+BN_HD int rows_per_part(int P, int nparts, int nl) {
+  const int nblk = (P + nl - 1) / nl;
+  return (nblk + nparts - 1) / nparts * nl;
+}
+// per-chain scratch (ints) of the ancestor updates.  anc_add_part: one row list per warp.
+// anc_del_team: two row lists per warp, then three dirty bitsets and four round flags.
+BN_HD int scratch_words(int P, int nparts, int nl) {
+  return 2 * rows_per_part(P, nparts, nl) * nparts + 3 * ((P + 31) / 32) + 4 + 28;
+}
 
 // nodes that have c as an ancestor (ascending), optionally c itself as well: the share of
 // `part` under a block-cyclic partition of the rows (blocks of Warp::NL rows; descendants
@@ -308,17 +314,13 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
 
 // The CTA of a chain has HELPER_WARPS extra warps parked on a named barrier; they take an
 // equal share of the rows of an ancestor update (the scan and the ORs are independent per row).
-constexpr int HELPER_WARPS = 3;
+constexpr int HELPER_WARPS = 7;
 enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_RECORDS = 2, HELPER_REPAIR = 3, HELPER_ANC_DEL = 4,
        HELPER_FILL_WH = 5 };
 // command block (ints): [0] op, [1..2] stream position, [3..4] ring limit, [5] n_haspar,
 // [6] TotalEdges, [7] Nagree, [8] node / parent, [9] child, [10] span limit (atomicMin target),
 // [11] child dropped below MaxPar
 constexpr int HELPER_WORDS = 12;
-BN_HD int rows_per_part(int P, int nparts) {  // most rows one warp can own (block-cyclic)
-  const int nblk = (P + Warp::NL - 1) / Warp::NL;
-  return (nblk + nparts - 1) / nparts * Warp::NL;
-}
 #if defined(__CUDACC__)
 __device__ __forceinline__ void cta_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"((HELPER_WARPS + 1) * 32) : "memory");
@@ -343,8 +345,9 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
     cta_bar(2);
     return;
   }
-#endif
+#else
   anc_add_part(p, m, j, c, m.scratch, 0, 1);
+#endif
 }
 
 
@@ -377,7 +380,7 @@ BN_HD Par8 load_par8(const ChainParams& p, const ChainMem& m, int d) {
 BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr, P = p.P, W = p.W, MP = p.max_par;
-  const int per = rows_per_part(P, nparts);
+  const int per = rows_per_part(P, nparts, Warp::NL);
   int* list = m.scratch + part * 2 * per;
   int* list2 = list + per;
   uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * per);
@@ -490,7 +493,7 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
   if (m.helper) nparts = HELPER_WARPS + 1;
 #endif
   {
-    uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * rows_per_part(p.P, nparts));
+    uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * rows_per_part(p.P, nparts, Warp::NL));
     for (int w = l; w < 3 * p.W + 4; w += Warp::NL) dirty[w] = 0u;  // three bitsets + four flags
     Warp::sync();
     if (l == 0) dirty[c >> 5] = 1u << (c & 31);
@@ -505,8 +508,9 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
     cta_bar(2);
     return;
   }
-#endif
+#else
   anc_del_team(p, m, c, 0, 1);
+#endif
 }
 
 // full build (chain start from a non-empty graph): Jacobi sweeps to the fixpoint
@@ -849,7 +853,8 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
     }
   }
 #undef BN_UAT
-  if (i >= hi) ovf = 1;  // the acceptance uniform must be in the ring as well
+  // the acceptance uniform must be in the ring as well, and the count must fit the record
+  if (i >= hi || i - q > REC_LEN_MASK) ovf = 1;
   const int ag = (!ovf && p.sim_edge[(int64_t)j + (int64_t)c * P]) ? 1 : 0;
   ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e; ws.t_full[slot] = full;
   ws.t_rec[slot] = (int)(i - q) | (type == 2 ? REC_TYPE : 0) | (cyc ? REC_CYC : 0) | (ovf ? REC_OVF : 0) |
@@ -986,7 +991,8 @@ __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem
       const int stale = repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[11], m.helper[8]);
       if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
     } else if (op == HELPER_ANC_ADD) {
-      anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * scratch_stride(p.P), part, HELPER_WARPS + 1);
+      anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * rows_per_part(p.P, HELPER_WARPS + 1, Warp::NL), part,
+                   HELPER_WARPS + 1);
     } else if (op == HELPER_ANC_DEL) {
       anc_del_team(p, m, m.helper[9], part, HELPER_WARPS + 1);
     } else if (op == HELPER_FILL_WH) {
@@ -1008,9 +1014,10 @@ BN_HD void team_records(const ChainParams& p, const ChainMem& m, const RoundCtx&
     cta_bar(2);
     return;
   }
-#endif
+#else
   for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL) build_record<KMAX>(p, m, rc, ubuf, ws, slot);
   Warp::sync();
+#endif
 }
 
 // returns the new span limit
@@ -1026,7 +1033,8 @@ BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& r
     cta_bar(2);
     return m.helper[10];
   }
-#endif
+  return 0;
+#else
   int lim = span_limit;
   for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL) {
     const int stale = repair_record(p, m, rc, ubuf, ws, slot, c, unfull, from);
@@ -1034,6 +1042,7 @@ BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& r
   }
   Warp::sync();
   return Warp::min(lim);
+#endif
 }
 
 // Walk the records from relative position *k: emits up to `want` slots, stops behind the
@@ -1259,8 +1268,8 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     t1 = cycle_now();
     s.cyc[2] += t1 - t0;
     if (n == 0) {
-      // one iteration outran the uniforms in the ring: retry with a full ring, then give up
-      if (ovf && k0 == 0) { if (s.need_full) s.status = 4; else s.need_full = 1; }
+      // one iteration needs more uniforms than a record can count: the sequential path takes it
+      if (ovf && k0 == 0) s.need_full = 1;
       break;
     }
     s.need_full = 0;
@@ -1311,17 +1320,17 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     s.cyc[0] += t1 - t0;
     s.windows++;
     // position-parallel rounds need `TotalEdges < 3` to be impossible
-    if (s.te_true >= 4 && s.te_m >= 3) {
+    if (s.te_true >= 4 && s.te_m >= 3 && !s.need_full) {
       run_round<KMAX>(p, m, s, rng, ws);
       continue;
     }
     // sequential windows (first iterations of a chain, tiny graphs)
-    int want = s.win;
+    int want = s.need_full ? 1 : s.win;
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     int overflow = 0;
     const int n = phase_a(p, m, s, rng, ws, want, &overflow);
     if (n == 0) {
-      if (s.need_full) { s.status = 4; break; }  // BN_ERR_NO_LEGAL_PROPOSAL
+      if (s.need_full) { s.status = 4; break; }  // BN_ERR_NO_LEGAL_PROPOSAL: one iteration outran the full ring
       s.need_full = 1;
       continue;
     }

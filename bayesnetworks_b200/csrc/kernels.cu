@@ -16,7 +16,7 @@ namespace bn {
 // have a provable shared-memory provenance and the state accesses compile to LDS/STS
 // instead of generic loads.
 template <int KMAX, bool ALL_SMEM>
-__global__ void __launch_bounds__((HELPER_WARPS + 1) * 32) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
+__global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra,
                                                    ChainSmemPlan sm, ChainResult* __restrict__ results) {
   __shared__ double ubuf[RNG_CAP];
   __shared__ WindowSlots ws;

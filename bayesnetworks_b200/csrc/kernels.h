@@ -11,7 +11,7 @@ struct ChainWorkspace {  // arrays over all chains of a run (device memory)
   int* par; int* npar; int* born; double* base;
   int* hp_list;
   uint32_t* anc; uint32_t* haspar;   // anc rows are anc_stride(W) words apart in global memory
-  int* scratch; int scratch_n;        // 4 * scratch_stride(P) ints per chain
+  int* scratch; int scratch_n;        // scratch_words(P, ...) ints per chain
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
   int* t_add; int* t_del; int* t_fn; int* t_fp;
   int* moves; int* edge_freq;

@@ -22,7 +22,7 @@ namespace bn {
 
 enum { RNG_WH = 0, RNG_RMT = 1, RNG_REPLAY = 2 };
 
-constexpr int RNG_CAP = 512;  // ring capacity (power of two)
+constexpr int RNG_CAP = 1024;  // ring capacity (power of two)
 
 struct RngStream {
   int kind;

@@ -30,7 +30,7 @@ extern "C" int emu_run_chain(
   p.prior_par = prior_par; p.prior_npar = prior_npar;
 
   std::vector<int> par((size_t)P * max_par), npar(P), born((size_t)P * max_par);
-  std::vector<int> scratch((size_t)4 * scratch_stride(P)), hp_list(P);
+  std::vector<int> scratch((size_t)scratch_words(P, 1, 1)), hp_list(P);
   std::vector<double> base(P);
   std::vector<uint32_t> anc_store((size_t)P * p.Ws + 4), haspar(p.W);
   uint32_t* anc = (uint32_t*)(((uintptr_t)anc_store.data() + 15) & ~(uintptr_t)15);
