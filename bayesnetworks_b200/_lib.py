@@ -49,6 +49,14 @@ class ChainStats(C.Structure):
                 ("phase_cycles", C.c_int64 * 6), ("slots_simulated", C.c_int64)]
 
 
+import numpy as _np
+CHAIN_STATS_DTYPE = _np.dtype([("uniforms", "<i8"), ("valid_iters", "<i8"), ("proposed", "<i4", (3,)),
+                               ("reject", "<i4", (3,)), ("n_nonpd", "<i4"), ("total_edges", "<i4"),
+                               ("status", "<i4"), ("windows", "<i4"), ("alg_bytes", "<i8"),
+                               ("phase_cycles", "<i8", (6,)), ("slots_simulated", "<i8")], align=True)
+assert CHAIN_STATS_DTYPE.itemsize == C.sizeof(ChainStats)
+
+
 class RunArgs(C.Structure):
     _fields_ = [("n_chains", C.c_int), ("rng_kind", C.c_int), ("seeds", _ip), ("replay", _dp),
                 ("replay_len", C.c_int64), ("initial_network", C.c_int), ("drop", C.c_int),

@@ -249,24 +249,28 @@ class Context:
         status = L.bn_run(self._h, C.byref(args), C.byref(tr), ptr(fpar), ptr(fnpar),
                           C.cast(stats, C.c_void_p), C.byref(ms))
         check(status)
+        # unused parent slots read -1; everything below is views / one vectorised pass (the
+        # per-chain Python work is part of every end-to-end step)
+        fpar = np.where(np.arange(mp, dtype=np.int32)[None, None, :] < fnpar[:, :, None], fpar, np.int32(-1))
+        st = np.frombuffer(stats, dtype=_lib.CHAIN_STATS_DTYPE, count=n_chains)
         out = []
         for ch in range(n_chains):
             r = int(n_rows[ch])
-            trace = {k: ints[k][ch, :r].copy() for k in ("iter", "ChangedNode", "movetype")}
-            trace["globalLL"] = gll[ch, :r].copy()
+            trace = {k: ints[k][ch, :r] for k in ("iter", "ChangedNode", "movetype")}
+            trace["globalLL"] = gll[ch, :r]
             for k in ("additions", "deletions", "FN", "FP"):
-                trace[k] = ints[k][ch, :r].copy()
-            s = stats[ch]
-            fp_ch = np.where(np.arange(mp)[None, :] < fnpar[ch][:, None], fpar[ch], -1).astype(np.int32)
+                trace[k] = ints[k][ch, :r]
+            s = st[ch]
             out.append(ChainResult(
-                trace=trace, uniforms=int(s.uniforms), valid_iters=int(s.valid_iters),
-                proposed=tuple(s.proposed), reject=tuple(s.reject), n_nonpd=int(s.n_nonpd),
-                total_edges=int(s.total_edges), windows=int(s.windows), alg_bytes=int(s.alg_bytes), phase_cycles=tuple(s.phase_cycles),
-                slots_simulated=int(s.slots_simulated),
-                final_parents=fp_ch,
-                final_npar=fnpar[ch].copy(),
-                accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])].copy(),
-                edge_freq=None if freq is None else freq[ch].copy()))
+                trace=trace, uniforms=int(s["uniforms"]), valid_iters=int(s["valid_iters"]),
+                proposed=tuple(s["proposed"].tolist()), reject=tuple(s["reject"].tolist()), n_nonpd=int(s["n_nonpd"]),
+                total_edges=int(s["total_edges"]), windows=int(s["windows"]), alg_bytes=int(s["alg_bytes"]),
+                phase_cycles=tuple(s["phase_cycles"].tolist()),
+                slots_simulated=int(s["slots_simulated"]),
+                final_parents=fpar[ch],
+                final_npar=fnpar[ch],
+                accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])],
+                edge_freq=None if freq is None else freq[ch]))
         return out, float(ms.value)
 
 

@@ -115,6 +115,28 @@ extern "C" int bn_trim_pool(void) {
   return BN_OK;
 }
 
+// BN_B200_TIMING=1: host wall-clock of the stages of bn_create*/bn_run on stderr
+#include <chrono>
+namespace {
+struct StageTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  const char* fn;
+  explicit StageTimer(const char* f) : fn(f) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("BN_B200_TIMING"); env = (e && e[0] == '1') ? 1 : 0; }
+    on = env == 1;
+    if (on) t = std::chrono::steady_clock::now();
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[bn timing] %s: %s %.3f ms\n", fn, what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
@@ -175,6 +197,7 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
                      int max_par, double phi, double omega, int device, bn_ctx** out) {
   if (!out) return fail(BN_ERR_BAD_ARG, "out is NULL");
   *out = nullptr;
+  StageTimer tm("ctx_begin");
   int rc = check_graph_args(n_samples, P, src, tgt, n_edges, node_type, max_par);
   if (rc) return rc;
   int ndev = bn_device_count();
@@ -184,10 +207,14 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
   bn_ctx* c = new bn_ctx();
   c->device = device;
   c->n_samples = n_samples; c->P = P; c->max_par = max_par; c->phi = phi; c->omega = omega;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->n_sms = prop.multiProcessorCount;
+  tm.lap("args+device");
+  // (cudaGetDeviceProperties costs 3-25 ms per call; one attribute is microseconds)
+  int n_sms = 0;
+  if (cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && n_sms > 0) c->n_sms = n_sms;
+  tm.lap("device attributes");
   *out = c;  // from here on the caller destroys on failure
   CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  tm.lap("stream create");
   c->stream = g_default_stream ? g_default_stream : c->own_stream;
 
   // parent lists edges[tgt-1].push_back(src-1), src/network.h:117-120
@@ -204,6 +231,7 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
     c->n_sim_edges++;
   }
   for (int p = 0; p < P; p++) types[p] = (uint8_t)node_type[p];
+  tm.lap("host graph arrays");
   CU_TRY(dalloc(c, &c->d_prior_par, par.size()));
   CU_TRY(dalloc(c, &c->d_prior_npar, npar.size()));
   CU_TRY(dalloc(c, &c->d_sim_edge, sim.size()));
@@ -212,10 +240,12 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
   CU_TRY(dalloc(c, &c->d_diag, (size_t)P));
   CU_TRY(dalloc(c, &c->d_mean, (size_t)P));
   CU_TRY(dalloc(c, &c->d_colsum, (size_t)P));
+  tm.lap("device allocations");
   CU_TRY(cudaMemcpy(c->d_prior_par, par.data(), par.size() * sizeof(int), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(c->d_prior_npar, npar.data(), npar.size() * sizeof(int), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(c->d_sim_edge, sim.data(), sim.size(), cudaMemcpyHostToDevice));
   CU_TRY(cudaMemcpy(c->d_node_type, types.data(), types.size(), cudaMemcpyHostToDevice));
+  tm.lap("graph upload");
   return BN_OK;
 }
 
@@ -223,12 +253,14 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
 static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc, const GramPlan& pl) {
   double *d_partial = nullptr, *d_scratch = nullptr;
   int* d_flag = nullptr;
+  StageTimer tm("ctx_build_gram");
   CU_TRY(pool_alloc((void**)&d_partial, (size_t)pl.workspace_bytes));
   cudaError_t e1 = pool_alloc((void**)&d_scratch, (size_t)c->P * GRAM_MEAN_MAX_CHUNKS * sizeof(double));
   cudaError_t e2 = pool_alloc((void**)&d_flag, sizeof(int));
   int rc = BN_OK;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(BN_ERR_OOM, "gram scratch allocation failed");
+  tm.lap("workspace");
   if (!rc) {
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
     cudaEventRecord(ev0, c->stream);
@@ -253,6 +285,7 @@ static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc,
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   pool_free(d_partial); pool_free(d_scratch); pool_free(d_flag);
+  tm.lap("launch + sync (incl. pending H2D)");
   return rc;
 }
 
@@ -263,10 +296,12 @@ extern "C" int bn_create(const double* X, int n_samples, int P, const int* src, 
   int rc = ctx_begin(n_samples, P, src, tgt, n_edges, node_type, max_par, phi, omega, device, out);
   if (rc) { if (out && *out) { bn_destroy(*out); *out = nullptr; } return rc; }
   bn_ctx* c = *out;
+  StageTimer tm("bn_create");
   const GramPlan pl = gram_plan(n_samples, P, c->n_sms);
   double* dXc = nullptr;
   cudaError_t e = pool_alloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
   if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the device copy of X"); }
+  tm.lap("alloc device copy of X");
   // column p of the R matrix is contiguous: one pitched copy into the padded buffer
   if (pl.ld_centered == n_samples)
     e = cudaMemcpyAsync(dXc, X, (size_t)n_samples * P * 8, cudaMemcpyHostToDevice, c->stream);
@@ -274,6 +309,7 @@ extern "C" int bn_create(const double* X, int n_samples, int P, const int* src, 
     e = cudaMemcpy2DAsync(dXc, (size_t)pl.ld_centered * 8, X, (size_t)n_samples * 8, (size_t)n_samples * 8,
                           (size_t)P, cudaMemcpyHostToDevice, c->stream);
   if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "H2D copy of X: %s", cudaGetErrorString(e));
+  tm.lap("enqueue H2D");
   if (!rc) rc = ctx_build_gram(c, dXc, pl.ld_centered, dXc, pl);  // centred in place
   pool_free(dXc);
   if (rc) { bn_destroy(c); *out = nullptr; }
@@ -522,6 +558,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
 
   const int64_t P = c->P, MP = c->max_par, W = (P + 31) / 32;
   const int64_t cap = trace->capacity > 0 ? trace->capacity : 1;
+  StageTimer tm("bn_run");
   DevBuf buf;
   ChainWorkspace w;
   memset(&w, 0, sizeof(w));
@@ -612,6 +649,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
 
   ChainResult* d_res = nullptr;
   CU_TRY(buf.alloc(&d_res, (size_t)nc));
+  tm.lap("workspace + seeds");
   cudaEvent_t ev0, ev1;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   cudaEventRecord(ev0, c->stream);
@@ -626,6 +664,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   if (msg) return fail(BN_ERR_UNSUPPORTED, "%s", msg);
   if (e != cudaSuccess) return fail(BN_ERR_CUDA, "chain kernel: %s", cudaGetErrorString(e));
   if (kernel_ms) *kernel_ms = ms;
+  tm.lap("chain kernel + sync");
 
   std::vector<ChainResult> res(nc);
   CU_TRY(cudaMemcpy(res.data(), d_res, sizeof(ChainResult) * nc, cudaMemcpyDeviceToHost));
@@ -666,6 +705,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   const cudaMemcpyKind fin_kind = dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (final_parents) CU_TRY(cudaMemcpy(final_parents, w.par, (size_t)(nc * P * MP) * 4, fin_kind));
   if (final_n_par) CU_TRY(cudaMemcpy(final_n_par, w.npar, (size_t)(nc * P) * 4, fin_kind));
+  tm.lap("results D2H");
   return rc;
 }
 

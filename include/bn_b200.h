@@ -160,12 +160,13 @@ typedef struct bn_chain_stats {
   int n_nonpd;             /* proposals whose parent Gram was not positive definite */
   int total_edges;         /* edges of the final graph */
   int status;              /* BN_OK or BN_ERR_NO_LEGAL_PROPOSAL */
-  int windows;             /* speculative windows executed */
+  int windows;             /* rounds (position-parallel) + sequential windows executed */
   int64_t alg_bytes;       /* sum over scored proposals of 8*(k'+1)(k'+2)/2 + 8: the algorithmic
                               gather bytes of the roofline (k' = parents in the scored set) */
-  int64_t phase_cycles[6]; /* SM cycles of the chain's warp per phase: uniform refill, draw replay,
-                              scoring + decision, commit, accepted additions, accepted deletions */
-  int64_t slots_simulated; /* iterations replayed speculatively (committed + discarded) */
+  int64_t phase_cycles[6]; /* SM cycles of the chain's warp per phase: uniform refill, position records
+                              (draw replay + scoring), walk + repair, commit, accepted additions,
+                              accepted deletions */
+  int64_t slots_simulated; /* iterations emitted by the record walk */
 } bn_chain_stats;
 
 typedef struct bn_run_args {
