@@ -162,8 +162,9 @@ BN_HD void hp_remove(ChainMem& m, int n_before, int c) {
 }
 
 // ---------------------------------------------------------------------------
-// Ancestor bitsets.  Row d = ancestors of node d, Ws words apart (Ws % 4 == 0, 16 B
-// aligned), processed in 128-bit chunks: `lpr` lanes share one row, so a warp updates
+// Ancestor bitsets.  Row d = ancestors of node d AND d itself (the reflexive closure: the
+// equations become row[d] = {d} u U_q row[q] over the parents q, one plain OR per parent),
+// Ws words apart (Ws % 4 == 0, 16 B aligned), processed in 128-bit chunks: `lpr` lanes share one row, so a warp updates
 // `rpp` = 32/lpr rows per pass (4 rows for 1,000 nodes).
 // ---------------------------------------------------------------------------
 struct alignas(16) U4 { uint32_t x, y, z, w; };
@@ -218,9 +219,12 @@ BN_HD int rows_per_part(int P, int nparts, int nl) {
   return (nblk + nparts - 1) / nparts * nl;
 }
 // per-chain scratch (ints) of the ancestor updates.  anc_add_part: one row list per warp.
-// anc_del_team: two row lists per warp, then three dirty bitsets and four round flags.
+// anc_del_team: two row lists per warp, the lost-ancestor bitset, three dirty bitsets and four
+// round flags (del_layout).
 BN_HD int scratch_words(int P, int nparts, int nl) {
-  return 2 * rows_per_part(P, nparts, nl) * nparts + 3 * ((P + 31) / 32) + 4 + 28;
+  const int W = (P + 31) / 32;
+  const int n = 2 * rows_per_part(P, nparts, nl) * nparts + 4 + (W + 3) / 4 * 4 + 3 * W + 4 + 1 + (W + 3) / 4 + 28;
+  return (n + 3) / 4 * 4;  // keeps every chain's block 16-byte aligned
 }
 
 // nodes that have c as an ancestor (ascending), optionally c itself as well: the share of
@@ -240,7 +244,7 @@ BN_HD int collect_desc_part(const ChainParams& p, const ChainMem& m, int c, int 
     for (int t = 0; t < 4; t++) {
       d[t] = d0 + t * step + l;
       flag[t] = 0;
-      if (d[t] < p.P) flag[t] = ((col[(uint32_t)d[t] * Ws] >> cb) & 1u) | ((include_self && d[t] == c) ? 1 : 0);
+      if (d[t] < p.P) flag[t] = ((col[(uint32_t)d[t] * Ws] >> cb) & 1u) & ((include_self || d[t] != c) ? 1u : 0u);
     }
 #pragma unroll
     for (int t = 0; t < 4; t++) {
@@ -251,22 +255,6 @@ BN_HD int collect_desc_part(const ChainParams& p, const ChainMem& m, int c, int 
   }
   Warp::sync();
   return n;
-}
-
-// anc[d] = union over the parents q of d of (anc[q] u {q}); all lanes, one row
-BN_HD void recompute_row(const ChainParams& p, ChainMem& m, int d, int chunks) {
-  U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
-  const int* pd = m.par + (int64_t)d * p.max_par;
-  const int kd = m.npar[d];
-  for (int ch = Warp::lane(); ch < chunks; ch += Warp::NL) {
-    U4 v = {0u, 0u, 0u, 0u};
-    for (int e = 0; e < kd; e++) {
-      const int q = pd[e];
-      v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
-      if (ch == (q >> 7)) v = with_bit(v, q & 127);
-    }
-    ad[ch] = v;
-  }
 }
 
 // after adding parent j to child c: every node in {c} u desc(c) gains anc[j] u {j}
@@ -280,8 +268,7 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
     // one 128-bit chunk per lane (up to 4,096 nodes): the source chunk stays in registers
     U4 a = {0u, 0u, 0u, 0u};
     if (li < g.chunks) {
-      a = aj[li];
-      if (li == (j >> 7)) a = with_bit(a, j & 127);
+      a = aj[li];  // row j holds j itself
     }
     for (int r0 = 0; r0 < n; r0 += 4 * g.rpp) {  // four rows in flight per lane group
       U4* ad[4];
@@ -302,9 +289,7 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
       if (r < n) {
         U4* ad = (U4*)(m.anc + (int64_t)list[r] * p.Ws);
         for (int ch = li; ch < g.chunks; ch += g.lpr) {
-          U4 v = or4(ad[ch], aj[ch]);
-          if (ch == (j >> 7)) v = with_bit(v, j & 127);
-          ad[ch] = v;
+          ad[ch] = or4(ad[ch], aj[ch]);
         }
       }
     }
@@ -367,136 +352,184 @@ BN_HD Par8 load_par8(const ChainParams& p, const ChainMem& m, int d) {
   return r;
 }
 
-// after removing a parent of child c (par[c] already updated).  If the remaining parents
-// still reach everything c reached, nothing changes anywhere (the common case in a graph
-// with redundant paths).  Otherwise the ancestor equations anc[d] = U_q (anc[q] u {q}) over
-// the parents q of d are re-solved on desc(c): in a DAG they have ONE solution, so chaotic
-// relaxation from the old rows converges to it.  Round r recomputes the rows that have a
-// parent whose row changed in round r-1 (change propagation -- with redundant paths the wave
-// dies out quickly); the rows of a round are independent, so every warp of the CTA relaxes
-// the descendants inside its own row range.  A row read while its owner rewrites it yields a
-// mix of old and new chunks, which is harmless: the owner marks it dirty, so the reader is
-// relaxed again next round with the final value.
+// after removing a parent of child c (par[c] already updated).  The new row of c follows from
+// its remaining parents; L = old row & ~new row are the ancestors c lost.  If L is empty nothing
+// changes anywhere (the common case in a graph with redundant paths).  Otherwise only bits of L
+// can disappear, and only from rows of desc(c).  Those rows are first cleared of L (a lower
+// bound of the truth), then the ancestor equations anc[d] = U_q (anc[q] u {q}) over the parents
+// q of d are iterated UPWARDS on the bits of L: round 0 evaluates every descendant, round r
+// those with a parent that regained a bit in round r-1.  In a DAG the equations have one
+// solution and the iteration reaches it from below; most descendants lose L for good, so the
+// regain wave is short (a few rounds) where a downward relaxation needs one round per level of
+// the loss wave.  Rows are owned by warps (block-cyclic); a row read while its owner updates
+// it yields a subset of its final value, which is harmless: the owner marks it dirty and the
+// reader is evaluated again next round.
+struct DelLayout { int* lists; U4* L; uint32_t* dirty; volatile int* flags; int* nzc; int per; };
+BN_HD DelLayout del_layout(const ChainParams& p, const ChainMem& m, int nparts) {
+  DelLayout d;
+  d.per = rows_per_part(p.P, nparts, Warp::NL);
+  int off = (2 * d.per * nparts + 3) / 4 * 4;
+  d.lists = m.scratch;
+  d.L = (U4*)(m.scratch + off);
+  off += (p.W + 3) / 4 * 4;
+  d.dirty = (uint32_t*)(m.scratch + off);
+  d.flags = (volatile int*)(d.dirty + 3 * p.W);
+  d.nzc = (int*)(d.dirty + 3 * p.W + 4);  // [0] = number of chunks where L != 0, then their indices
+  return d;
+}
+BN_HD U4 andn4(U4 a, U4 b) { U4 r; r.x = a.x & ~b.x; r.y = a.y & ~b.y; r.z = a.z & ~b.z; r.w = a.w & ~b.w; return r; }
+BN_HD U4 and4(U4 a, U4 b) { U4 r; r.x = a.x & b.x; r.y = a.y & b.y; r.z = a.z & b.z; r.w = a.w & b.w; return r; }
+BN_HD bool nz4(U4 a) { return (a.x | a.y | a.z | a.w) != 0u; }
+
 BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts) {
-  const RowGeom g = row_geom(p);
-  const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr, P = p.P, W = p.W, MP = p.max_par;
-  const int per = rows_per_part(P, nparts, Warp::NL);
-  int* list = m.scratch + part * 2 * per;
-  int* list2 = list + per;
-  uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * per);
-  volatile int* flags = (volatile int*)(dirty + 3 * W);
+  const int l = Warp::lane(), W = p.W, MP = p.max_par;
+  const DelLayout lay = del_layout(p, m, nparts);
+  int* list = lay.lists + part * 2 * lay.per;
+  int* list2 = list + lay.per;
   const int n = collect_desc_part(p, m, c, 0, list, part, nparts);  // old column c: rows this warp owns
   const uint32_t lt = (l == 31) ? 0x7fffffffu : ((1u << l) - 1u);
-  for (int round = 0;; round++) {
-    const uint32_t* dprev = dirty + (round % 3) * W;
-    uint32_t* dnext = dirty + ((round + 1) % 3) * W;
-    if (part == 0) {  // nobody reads or writes these during this round
-      uint32_t* dclr = dirty + ((round + 2) % 3) * W;
-      for (int w = l; w < W; w += Warp::NL) dclr[w] = 0u;
-      if (l == 0) flags[(round + 2) % 4] = 0;
+  // L is usually confined to one or two 128-bit chunks: a lane takes one (row, non-zero chunk)
+  // pair, so a pass covers 32 / lpr rows with lpr = nnz rounded up to a power of two
+  const int nnz = lay.nzc[0];
+  int lpr = 1;
+  while (lpr < nnz && lpr < Warp::NL) lpr <<= 1;
+  const int rpp = Warp::NL / lpr, sub = l / lpr, li = l % lpr;
+  const uint32_t gm = (lpr >= 32 ? 0xffffffffu : ((1u << lpr) - 1u)) << (sub * lpr);
+  // clear L from the rows of the descendants
+  for (int r0 = 0; r0 < n; r0 += rpp) {
+    const int r = r0 + sub;
+    if (r < n) {
+      U4* ad = (U4*)(m.anc + (uint32_t)list[r] * (uint32_t)p.Ws);
+      for (int t = li; t < nnz; t += lpr) {
+        const int ch = lay.nzc[1 + t];
+        ad[ch] = andn4(ad[ch], lay.L[ch]);
+      }
     }
-    int nt = 0;
-    for (int i0 = 0; i0 < n; i0 += Warp::NL) {
-      const int i = i0 + l;
-      const int d = (i < n) ? list[i] : -1;
-      int touched = 0;
-      if (d >= 0) {
-        if (MP <= 8) {
-          // unused slots of a parent list hold -1: all eight dirty words load independently
-          const Par8 pq = load_par8(p, m, d);
+  }
+  team_sync(m);
+  for (int round = 0;; round++) {
+    const uint32_t* dprev = lay.dirty + (round % 3) * W;
+    uint32_t* dnext = lay.dirty + ((round + 1) % 3) * W;
+    if (part == 0) {  // nobody reads or writes these during this round
+      uint32_t* dclr = lay.dirty + ((round + 2) % 3) * W;
+      for (int w = l; w < W; w += Warp::NL) dclr[w] = 0u;
+      if (l == 0) lay.flags[(round + 2) % 4] = 0;
+    }
+    const int* rows = list;
+    int nt = n;
+    if (round > 0) {
+      // rows with a parent that regained a bit last round
+      rows = list2;
+      nt = 0;
+      for (int i0 = 0; i0 < n; i0 += Warp::NL) {
+        const int i = i0 + l;
+        const int d = (i < n) ? list[i] : -1;
+        int touched = 0;
+        if (d >= 0) {
+          if (MP <= 8) {
+            // unused slots of a parent list hold -1: all eight dirty words load independently
+            const Par8 pq = load_par8(p, m, d);
 #pragma unroll
-          for (int e = 0; e < 8; e++)
-            if (pq.q[e] >= 0) touched |= (dprev[pq.q[e] >> 5] >> (pq.q[e] & 31)) & 1u;
-        } else {
-          const int kd = m.npar[d];
-          const int* pd = m.par + (int64_t)d * MP;
-          for (int e = 0; e < kd; e++) {
-            const int q = pd[e];
-            touched |= (dprev[q >> 5] >> (q & 31)) & 1u;
+            for (int e = 0; e < 8; e++)
+              if (pq.q[e] >= 0) touched |= (dprev[pq.q[e] >> 5] >> (pq.q[e] & 31)) & 1u;
+          } else {
+            const int kd = m.npar[d];
+            const int* pd = m.par + (int64_t)d * MP;
+            for (int e = 0; e < kd; e++) {
+              const int q = pd[e];
+              touched |= (dprev[q >> 5] >> (q & 31)) & 1u;
+            }
           }
         }
+        const uint32_t mask = Warp::ballot(touched);
+        if (touched) list2[nt + popc32(mask & lt)] = d;
+        nt += popc32(mask);
       }
-      const uint32_t mask = Warp::ballot(touched);
-      if (touched) list2[nt + popc32(mask & lt)] = d;
-      nt += popc32(mask);
+      Warp::sync();
     }
-    Warp::sync();
     int any = 0;
-    for (int r0 = 0; r0 < nt; r0 += g.rpp) {
+    for (int r0 = 0; r0 < nt; r0 += rpp) {
       const int r = r0 + sub;
       int changed = 0, d = 0;
       if (r < nt) {
-        d = list2[r];
-        U4* ad = (U4*)(m.anc + (int64_t)d * p.Ws);
-        if (MP <= 8) {
-          const Par8 pq = load_par8(p, m, d);
-          for (int ch = li; ch < g.chunks; ch += g.lpr) {
-            U4 v = {0u, 0u, 0u, 0u};
+        d = rows[r];
+        U4* ad = (U4*)(m.anc + (uint32_t)d * (uint32_t)p.Ws);
+        for (int t = li; t < nnz; t += lpr) {
+          const int ch = lay.nzc[1 + t];
+          const U4 Lc = lay.L[ch];
+          U4 v = {0u, 0u, 0u, 0u};
+          if (MP <= 8) {
+            const Par8 pq = load_par8(p, m, d);
 #pragma unroll
             for (int e = 0; e < 8; e++) {
               const int q = pq.q[e];
-              if (q >= 0) {
-                v = or4(v, ((const U4*)(m.anc + (uint32_t)q * (uint32_t)p.Ws))[ch]);
-                if (ch == (q >> 7)) v = with_bit(v, q & 127);
-              }
+              if (q >= 0) v = or4(v, ((const U4*)(m.anc + (uint32_t)q * (uint32_t)p.Ws))[ch]);
             }
-            if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
-          }
-        } else {
-          const int kd = m.npar[d];
-          const int* pd = m.par + (int64_t)d * MP;
-          for (int ch = li; ch < g.chunks; ch += g.lpr) {
-            U4 v = {0u, 0u, 0u, 0u};
+          } else {
+            const int kd = m.npar[d];
+            const int* pd = m.par + (int64_t)d * MP;
             for (int e = 0; e < kd; e++) {
               const int q = pd[e];
               v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
-              if (ch == (q >> 7)) v = with_bit(v, q & 127);
             }
-            if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
           }
+          const U4 cur = ad[ch];
+          const U4 gain = andn4(and4(v, Lc), cur);
+          if (nz4(gain)) { ad[ch] = or4(cur, gain); changed = 1; }
         }
       }
       const uint32_t mask = Warp::ballot(changed);
-      const uint32_t gm = (g.lpr >= 32 ? 0xffffffffu : ((1u << g.lpr) - 1u)) << (sub * g.lpr);
       if (r < nt && li == 0 && (mask & gm)) atomic_or_u32(&dnext[d >> 5], 1u << (d & 31));
       any |= (mask != 0u);
       Warp::sync();  // later passes of this warp see the new rows
     }
-    if (any && l == 0) flags[round % 4] = 1;
+    if (any && l == 0) lay.flags[round % 4] = 1;
     team_sync(m);
-    if (flags[round % 4] == 0) break;
+    if (lay.flags[round % 4] == 0) break;
   }
 }
 
 BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane();
+  int nparts = 1;
+#if defined(__CUDA_ARCH__)
+  if (m.helper) nparts = HELPER_WARPS + 1;
+#endif
+  const DelLayout lay = del_layout(p, m, nparts);
   {
-    // new row of c from its remaining parents; unchanged -> nothing else can change
+    // new row of c from its remaining parents (a subset of the old row); L = what it lost
     U4* ac = (U4*)(m.anc + (int64_t)c * p.Ws);
     const int* pc = m.par + (int64_t)c * p.max_par;
     const int kc = m.npar[c];
     int changed = 0;
     for (int ch = l; ch < g.chunks; ch += Warp::NL) {
       U4 v = {0u, 0u, 0u, 0u};
+      if (ch == (c >> 7)) v = with_bit(v, c & 127);
       for (int e = 0; e < kc; e++) {
         const int q = pc[e];
         v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
-        if (ch == (q >> 7)) v = with_bit(v, q & 127);
       }
-      if (ne4(v, ac[ch])) { ac[ch] = v; changed = 1; }
+      const U4 lost = andn4(ac[ch], v);
+      lay.L[ch] = lost;
+      if (nz4(lost)) { ac[ch] = v; changed = 1; }
     }
     if (Warp::ballot(changed) == 0u) return;
   }
-  int nparts = 1;
-#if defined(__CUDA_ARCH__)
-  if (m.helper) nparts = HELPER_WARPS + 1;
-#endif
+  for (int w = l; w < 3 * p.W + 4; w += Warp::NL) lay.dirty[w] = 0u;  // three bitsets + four flags
+  Warp::sync();
   {
-    uint32_t* dirty = (uint32_t*)(m.scratch + nparts * 2 * rows_per_part(p.P, nparts, Warp::NL));
-    for (int w = l; w < 3 * p.W + 4; w += Warp::NL) dirty[w] = 0u;  // three bitsets + four flags
-    Warp::sync();
-    if (l == 0) dirty[c >> 5] = 1u << (c & 31);
+    // indices of the chunks where something was lost
+    const uint32_t lt = (l == 31) ? 0x7fffffffu : ((1u << l) - 1u);
+    int nnz = 0;
+    for (int ch0 = 0; ch0 < g.chunks; ch0 += Warp::NL) {
+      const int ch = ch0 + l;
+      const int nz = (ch < g.chunks) && nz4(lay.L[ch]);
+      const uint32_t mask = Warp::ballot(nz);
+      if (nz) lay.nzc[1 + nnz + popc32(mask & lt)] = ch;
+      nnz += popc32(mask);
+    }
+    if (l == 0) lay.nzc[0] = nnz;
     Warp::sync();
   }
 #if defined(__CUDA_ARCH__)
@@ -513,12 +546,20 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
 #endif
 }
 
+// empty graph: every row holds its own node only
+BN_HD void anc_reset(const ChainParams& p, ChainMem& m) {
+  const int l = Warp::lane();
+  for (int64_t i = l; i < (int64_t)p.P * p.Ws; i += Warp::NL) m.anc[i] = 0u;
+  Warp::sync();
+  for (int d = l; d < p.P; d += Warp::NL) m.anc[(int64_t)d * p.Ws + (d >> 5)] = 1u << (d & 31);
+  Warp::sync();
+}
+
 // full build (chain start from a non-empty graph): Jacobi sweeps to the fixpoint
 BN_HD void anc_build_all(const ChainParams& p, ChainMem& m) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane(), P = p.P;
-  for (int64_t i = l; i < (int64_t)P * p.Ws; i += Warp::NL) m.anc[i] = 0u;
-  Warp::sync();
+  anc_reset(p, m);
   for (int round = 0; round <= P; round++) {
     int changed = 0;
     for (int d = 0; d < P; d++) {
@@ -528,10 +569,10 @@ BN_HD void anc_build_all(const ChainParams& p, ChainMem& m) {
       const int* pd = m.par + (int64_t)d * p.max_par;
       for (int ch = l; ch < g.chunks; ch += Warp::NL) {
         U4 v = {0u, 0u, 0u, 0u};
+        if (ch == (d >> 7)) v = with_bit(v, d & 127);
         for (int e = 0; e < kd; e++) {
           const int q = pd[e];
           v = or4(v, ((const U4*)(m.anc + (int64_t)q * p.Ws))[ch]);
-          if (ch == (q >> 7)) v = with_bit(v, q & 127);
         }
         if (ne4(v, ad[ch])) { ad[ch] = v; changed = 1; }
       }
@@ -573,9 +614,7 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   s.n_haspar = Warp::shfl(s.n_haspar, 0);
   Warp::sync();
   if (s.te_true > 0) anc_build_all(p, m);
-  else {
-    for (int64_t i = l; i < (int64_t)P * p.Ws; i += Warp::NL) m.anc[i] = 0u;
-  }
+  else anc_reset(p, m);
   // base scores
   s.n_nonpd = 0;
   for (int c = l; c < P; c += Warp::NL) {
