@@ -1084,97 +1084,45 @@ BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& r
 #endif
 }
 
-// Walk the records from relative position *k: emits up to `want` slots, stops behind the
-// first accepted one.  Returns the number of slots; *ovf when the walk hit an overflowed
-// record.
-BN_HD int walk_emit(const ChainParams& p, const ChainScalars& s, const RngStream& rng, WindowSlots& ws,
-                    int64_t round_pos, int* k_io, int span_limit, int want, int* ovf) {
-  const int l = Warp::lane();
-  int k = *k_io, v = s.valid, n = 0;
-  *ovf = 0;
-  while (n < want && k < span_limit) {
-    const int rec = ws.t_rec[k];
-    if (rec & REC_OVF) { *ovf = 1; break; }
-    // `valid` is only assigned by additions (src/bayesnet_mcmc.cpp:50-52)
-    const int valid = (rec & REC_TYPE) ? v : !(rec & REC_CYC);
-    if (l == 0) ws.s_k[n] = k | (valid << 16);
-    v = valid;
-    k += (rec & REC_LEN_MASK) + valid;  // the acceptance uniform is drawn for valid iterations only
-    n++;
-    if (valid && (rec & REC_ACC)) break;
-  }
-  Warp::sync();
-  const int fp_true = s.te_true - s.agree_true, fn_true = p.n_sim_edges - s.agree_true;
-  for (int q0 = 0; q0 < n; q0 += Warp::NL) {
-    const int q = q0 + l;
-    if (q < n) {
-      const int sk = ws.s_k[q];
-      const int kk = sk & 0xffff, valid = sk >> 16;
-      const int rec = ws.t_rec[kk];
-      const int type = (rec & REC_TYPE) ? 2 : 1;
-      const int64_t at = round_pos + kk + (rec & REC_LEN_MASK);
-      ws.child[q] = ws.t_c[kk]; ws.parent[q] = ws.t_j[kk]; ws.pos[q] = ws.t_e[kk];
-      ws.type[q] = (signed char)type; ws.valid[q] = (signed char)valid;
-      const int te_m = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
-      ws.te_m[q] = te_m;
-      ws.u_acc[q] = valid ? rng.ubuf[at & (RNG_CAP - 1)] : 0.0;
-      ws.pos_after[q] = at + (valid ? 1 : 0);
-      if (valid) {
-        // members left by checker()'s LogPrior() on the proposed graph, src/network.h:333
-        const int ag = (rec & REC_AG) ? 1 : 0;
-        const int ag_new = s.agree_true + (type == 1 ? ag : -ag);
-        ws.fp_m[q] = te_m - ag_new; ws.fn_m[q] = p.n_sim_edges - ag_new;
-        ws.new_score[q] = ws.t_score[kk];
-        ws.kk[q] = rec >> REC_KK_SHIFT;
-        ws.nonpd[q] = (rec & REC_NPD) ? 1 : 0;
-        ws.accept[q] = (rec & REC_ACC) ? 1 : 0;
-      } else {
-        // invalid: only OldLogPrior ran, the members describe the current graph
-        ws.fp_m[q] = fp_true; ws.fn_m[q] = fn_true;
-        ws.new_score[q] = 0.0; ws.kk[q] = 0; ws.nonpd[q] = 0; ws.accept[q] = 0;
-      }
-    }
-  }
-  Warp::sync();
-  *k_io = k;
-  return n;
-}
-
 // ---------------------------------------------------------------------------
 // Commit: counters, trace rows, and the accepted move if any (warp-uniform).
 // ---------------------------------------------------------------------------
-BN_HD void write_row(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
-                     const WindowSlots& ws, int i, int additions, int deletions) {
+BN_HD void write_row_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it, int child,
+                          int type, int fn, int fp, int additions, int deletions) {
   if (!s.gll_ok) { s.gll = sum_base(p, m); s.gll_ok = 1; }
   if (s.n_rows < p.trace_capacity) {
     if (Warp::lane() == 0) {
       const int r = s.n_rows;
       m.t_iter[r] = (int)it;
-      m.t_changed[r] = ws.child[i];
-      m.t_movetype[r] = ws.type[i];
+      m.t_changed[r] = child;
+      m.t_movetype[r] = type;
       m.t_gll[r] = s.gll;
       m.t_add[r] = additions;
       m.t_del[r] = deletions;
-      m.t_fn[r] = ws.fn_m[i];
-      m.t_fp[r] = ws.fp_m[i];
+      m.t_fn[r] = fn;
+      m.t_fp[r] = fp;
     }
     s.n_rows++;
   }
 }
+BN_HD void write_row(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
+                     const WindowSlots& ws, int i, int additions, int deletions) {
+  write_row_vals(p, m, s, it, ws.child[i], ws.type[i], ws.fn_m[i], ws.fp_m[i], additions, deletions);
+}
 
-BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
-                      const WindowSlots& ws, int i) {
-  const int c = ws.child[i], j = ws.parent[i], MP = p.max_par, l = Warp::lane();
+BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it, int type, int c,
+                           int j, int del, double new_score) {
+  const int MP = p.max_par, l = Warp::lane();
   int* pc = m.par + (int64_t)c * MP;
   int* bc = m.born + (int64_t)c * MP;
   const int k = m.npar[c];
   const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
   Warp::sync();
-  if (ws.type[i] == 1) {
+  if (type == 1) {
     if (l == 0) {
       pc[k] = j; bc[k] = (int)first_counted; m.npar[c] = k + 1;
-      m.base[c] = ws.new_score[i];
+      m.base[c] = new_score;
     }
     if (k == 0) {
       Warp::sync();
@@ -1186,7 +1134,6 @@ BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_
     Warp::sync();
     anc_after_add(p, m, j, c);
   } else {
-    const int del = ws.pos[i];
     if (l == 0) {
       if (m.edge_freq) {
         const int64_t cnt = first_counted - bc[del];
@@ -1195,7 +1142,7 @@ BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_
       for (int e = del; e + 1 < k; e++) { pc[e] = pc[e + 1]; bc[e] = bc[e + 1]; }
       pc[k - 1] = -1;
       m.npar[c] = k - 1;
-      m.base[c] = ws.new_score[i];
+      m.base[c] = new_score;
     }
     if (k == 1) {
       Warp::sync();
@@ -1210,12 +1157,17 @@ BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_
   if (s.n_moves < p.moves_capacity) {
     if (l == 0) {
       int* mv = m.moves + (int64_t)s.n_moves * 4;
-      mv[0] = (int)it; mv[1] = ws.type[i]; mv[2] = c; mv[3] = j;
+      mv[0] = (int)it; mv[1] = type; mv[2] = c; mv[3] = j;
     }
   }
   s.n_moves++;
   s.gll_ok = 0;
   Warp::sync();
+}
+
+BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
+                      const WindowSlots& ws, int i) {
+  apply_move_vals(p, m, s, it, ws.type[i], ws.child[i], ws.parent[i], ws.pos[i], ws.new_score[i]);
 }
 
 // Commit slots [0, ncommit): all but possibly the last are rejections/invalid.
@@ -1282,9 +1234,97 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
   Warp::sync();
 }
 
-// ---------------------------------------------------------------------------
-// The whole chain.
-// ---------------------------------------------------------------------------
+// One epoch of a round: walk the records from relative position *k_io (at most `want`
+// iterations, stopping behind the first accepted one) and commit them -- the same bookkeeping
+// as commit(), with the slot of iteration s.iter + q living in the registers of lane q.
+// Returns the number of iterations committed; *accepted / *acc_c / *acc_type describe the
+// accepted move, *ovf an overflowed record in front of the walk.
+BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const WindowSlots& ws, int64_t round_pos,
+                      int* k_io, int span_limit, int want, int* ovf, int* accepted, int* acc_c, int* acc_type) {
+  const int l = Warp::lane();
+  int k = *k_io, v = s.valid, n = 0, myk = 0, myvalid = 0, acc = 0, k_acc = 0;
+  *ovf = 0;
+  while (n < want && k < span_limit) {
+    const int rec = ws.t_rec[k];
+    if (rec & REC_OVF) { *ovf = 1; break; }
+    // `valid` is only assigned by additions (src/bayesnet_mcmc.cpp:50-52)
+    const int valid = (rec & REC_TYPE) ? v : !(rec & REC_CYC);
+    if (l == n) { myk = k; myvalid = valid; }
+    v = valid;
+    k_acc = k;
+    k += (rec & REC_LEN_MASK) + valid;  // the acceptance uniform is drawn for valid iterations only
+    n++;
+    if (valid && (rec & REC_ACC)) { acc = 1; break; }
+  }
+  *accepted = acc;
+  if (n == 0) return 0;
+  const long long tc = cycle_now();
+  const int last = n - 1;
+  const bool in = l < n;
+  const int rec = in ? ws.t_rec[myk] : 0;
+  const int child = in ? ws.t_c[myk] : 0;
+  const int type = (rec & REC_TYPE) ? 2 : 1;
+  const bool valid = in && myvalid;
+  const int it = (int)s.iter + l;  // n_iter is an int
+  const bool counted = valid && it >= p.drop;  // src/network.h:331, src/bayesnet_mcmc.cpp:58
+  const uint32_t accbit = acc ? (1u << last) : 0u;  // only the last slot can be an acceptance
+  const uint32_t m_valid = Warp::ballot(valid);
+  const uint32_t m_inval = Warp::ballot(in && !valid);
+  const uint32_t m_p1 = Warp::ballot(counted && type == 1);
+  const uint32_t m_p2 = Warp::ballot(counted && type == 2);
+  const uint32_t m_r1 = m_p1 & ~accbit, m_r2 = m_p2 & ~accbit;
+  const uint32_t m_npd = Warp::ballot(valid && (rec & REC_NPD));
+  const uint32_t m_log = Warp::ballot(valid && (it % p.output_every == 0));  // :63-65
+  const int kk = valid ? (rec >> REC_KK_SHIFT) : 0;
+  const int bytes = Warp::sum(valid ? 4 * (kk + 1) * (kk + 2) + 8 : 0);
+  // members left by the last LogPrior(): the proposed graph for valid iterations
+  // (checker(), src/network.h:333), the current graph otherwise
+  const int ag = (rec & REC_AG) ? 1 : 0;
+  const int te_m = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
+  const int ag_new = valid ? s.agree_true + (type == 1 ? ag : -ag) : s.agree_true;
+  const int fp_m = te_m - ag_new, fn_m = p.n_sim_edges - ag_new;
+  // rows of rejected iterations (pre-move graph), in order
+  uint32_t lg = m_log & ~accbit;
+  while (lg) {
+    const int b = ffs32(lg) - 1;
+    lg &= lg - 1;
+    const uint32_t upto = (b == 31) ? 0xffffffffu : ((2u << b) - 1u);
+    write_row_vals(p, m, s, s.iter + b, Warp::shfl(child, b), Warp::shfl(type, b), Warp::shfl(fn_m, b),
+                   Warp::shfl(fp_m, b),
+                   (s.proposed[1] + popc32(m_p1 & upto)) - (s.reject[1] + popc32(m_r1 & upto)),
+                   (s.proposed[2] + popc32(m_p2 & upto)) - (s.reject[2] + popc32(m_r2 & upto)));
+  }
+  s.valid_iters += popc32(m_valid);
+  s.alg_bytes += bytes;
+  s.proposed[1] += popc32(m_p1); s.proposed[2] += popc32(m_p2);
+  s.reject[0] += popc32(m_inval);  // notValid(), src/network.h:434-437 (not guarded by drop)
+  s.reject[1] += popc32(m_r1); s.reject[2] += popc32(m_r2);
+  s.n_nonpd += popc32(m_npd);
+  const int te_last = Warp::shfl(te_m, last), fp_last = Warp::shfl(fp_m, last), fn_last = Warp::shfl(fn_m, last);
+  long long dt = 0;
+  if (acc) {
+    const int c = ws.t_c[k_acc], a_type = (ws.t_rec[k_acc] & REC_TYPE) ? 2 : 1;
+    const long long ta = cycle_now();
+    apply_move_vals(p, m, s, s.iter + last, a_type, c, ws.t_j[k_acc], ws.t_e[k_acc], ws.t_score[k_acc]);
+    dt = cycle_now() - ta;
+    s.cyc[a_type == 1 ? 4 : 5] += dt;
+    if (m_log & accbit)
+      write_row_vals(p, m, s, s.iter + last, c, a_type, fn_last, fp_last, s.proposed[1] - s.reject[1],
+                     s.proposed[2] - s.reject[2]);
+    *acc_c = c; *acc_type = a_type;
+  }
+  s.valid = v;
+  s.te_m = te_last; s.fp_m = fp_last; s.fn_m = fn_last;
+  s.read_pos = round_pos + k;
+  s.iter += n;
+  // the caller charges the whole call to the walk: move the commit part and the move over
+  const long long tcommit = cycle_now() - tc;
+  s.cyc[3] += tcommit - dt;
+  s.cyc[2] -= tcommit;
+  *k_io = k;
+  return n;
+}
+
 // One round: records for REPLAY_POS positions, then walk / commit / repair epochs.
 template <int KMAX>
 BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng, WindowSlots& ws) {
@@ -1298,14 +1338,13 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   int k = 0, span_limit = REPLAY_POS;
   for (;;) {
     t0 = cycle_now();
-    int want = WIN;
+    int want = WIN < Warp::NL ? WIN : Warp::NL;  // one lane per iteration of the epoch
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     if (want <= 0) break;
-    int ovf = 0;
-    const int k0 = k;
-    const int n = walk_emit(p, s, rng, ws, rc.pos, &k, span_limit, want, &ovf);
-    t1 = cycle_now();
-    s.cyc[2] += t1 - t0;
+    int ovf = 0, accepted = 0, c = 0, type = 0;
+    const int k0 = k, nh0 = s.n_haspar;
+    const int n = round_epoch(p, m, s, ws, rc.pos, &k, span_limit, want, &ovf, &accepted, &c, &type);
+    s.cyc[2] += cycle_now() - t0;
     if (n == 0) {
       // one iteration needs more uniforms than a record can count: the sequential path takes it
       if (ovf && k0 == 0) s.need_full = 1;
@@ -1313,11 +1352,6 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     }
     s.need_full = 0;
     s.slots_sim += n;
-    const int last = n - 1;
-    const int accepted = ws.valid[last] && ws.accept[last];
-    const int c = ws.child[last], type = ws.type[last], nh0 = s.n_haspar;
-    commit(p, m, s, ws, n);
-    s.cyc[3] += cycle_now() - t1;
     if (ovf || k >= span_limit) break;
     if (accepted) {
       // moves that invalidate every record: the set of nodes with parents changed (deletion
