@@ -21,7 +21,8 @@ BN_RNG_WH, BN_RNG_RMT, BN_RNG_REPLAY = 0, 1, 2
 
 EXPORTED_SYMBOLS = (
     "bn_last_error", "bn_abi_version", "bn_device_count", "bn_create", "bn_create_from_device",
-    "bn_create_from_stats", "bn_destroy", "bn_trim_pool", "bn_set_stream", "bn_set_default_stream", "bn_get_stats", "bn_get_gram_ms",
+    "bn_create_from_stats", "bn_block_colsum_device", "bn_block_gram_device", "bn_create_from_stats_device",
+    "bn_destroy", "bn_trim_pool", "bn_set_stream", "bn_set_default_stream", "bn_get_stats", "bn_get_gram_ms",
     "bn_get_launch_count", "bn_score_nodes", "bn_score_all_proposals",
     "bn_score_all_proposals_device", "bn_run", "bn_main_fun",
 )
@@ -89,6 +90,12 @@ def lib() -> C.CDLL:
     L.bn_create_from_stats.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                        C.POINTER(C.c_void_p)]
+    L.bn_block_colsum_device.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    L.bn_block_gram_device.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.POINTER(C.c_float)]
+    L.bn_create_from_stats_device.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                              C.POINTER(C.c_void_p)]
     L.bn_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.bn_set_default_stream.argtypes = [C.c_void_p]
     L.bn_get_stats.argtypes = [C.c_void_p] * 5

@@ -114,6 +114,18 @@ class Context:
                                               float(omega), int(device), C.byref(h)))
         return cls(h, int(n_samples), p, int(max_par))
 
+    @classmethod
+    def from_stats_device(cls, n_samples, n_nodes, d_mean, d_centered_gram, graph_source, graph_target,
+                          graph_node_type, max_par=50, phi=1.0, omega=6.9, device=0):
+        """Sufficient statistics already in HBM (device pointers): the row-sharded Gram path."""
+        src, tgt, nt = cls._graph_args(graph_source, graph_target, graph_node_type, n_nodes)
+        h = C.c_void_p()
+        check(_lib.lib().bn_create_from_stats_device(int(n_samples), int(n_nodes), C.c_void_p(int(d_mean)),
+                                                     C.c_void_p(int(d_centered_gram)), ptr(src), ptr(tgt),
+                                                     len(src), ptr(nt), int(max_par), float(phi), float(omega),
+                                                     int(device), C.byref(h)))
+        return cls(h, int(n_samples), int(n_nodes), int(max_par))
+
     def close(self):
         if self._h is not None and self._h.value:
             _lib.lib().bn_destroy(self._h)
@@ -272,6 +284,21 @@ class Context:
                 accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])],
                 edge_freq=None if freq is None else freq[ch]))
         return out, float(ms.value)
+
+
+def block_colsum_device(data_ptr, ld, n_rows, n_nodes, out_ptr, device=0, stream=0):
+    """Column sums of one row block of X (device pointers); see ``bn_block_colsum_device``."""
+    check(_lib.lib().bn_block_colsum_device(C.c_void_p(int(data_ptr)), int(ld), int(n_rows), int(n_nodes),
+                                            C.c_void_p(int(out_ptr)), int(device), C.c_void_p(int(stream))))
+
+
+def block_gram_device(data_ptr, ld, n_rows, n_nodes, mean_ptr, out_ptr, device=0, stream=0):
+    """One row block's part of the centred cross-product matrix (device pointers); returns kernel ms."""
+    ms = C.c_float(0)
+    check(_lib.lib().bn_block_gram_device(C.c_void_p(int(data_ptr)), int(ld), int(n_rows), int(n_nodes),
+                                          C.c_void_p(int(mean_ptr)), C.c_void_p(int(out_ptr)), int(device),
+                                          C.c_void_p(int(stream)), C.byref(ms)))
+    return float(ms.value)
 
 
 # ---------------------------------------------------------------------------

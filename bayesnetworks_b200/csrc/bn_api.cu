@@ -137,6 +137,12 @@ struct StageTimer {
 };
 }  // namespace
 
+__global__ void colsum_from_mean_kernel(const double* __restrict__ mean, int n_samples, int P,
+                                        double* __restrict__ colsum) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) colsum[p] = mean[p] * (double)n_samples;
+}
+
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
@@ -353,6 +359,101 @@ extern "C" int bn_create_from_stats(int n_samples, int P, const double* mean, co
   }
   if (e != cudaSuccess) {
     rc = fail(BN_ERR_CUDA, "upload of sufficient statistics: %s", cudaGetErrorString(e));
+    bn_destroy(c); *out = nullptr;
+  }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// row-sharded sufficient statistics (config 5)
+// ---------------------------------------------------------------------------
+extern "C" int bn_block_colsum_device(const double* dX, int64_t ld, int n_rows, int P, double* d_out_sum,
+                                      int device, void* stream) {
+  if (!dX || !d_out_sum) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  if (n_rows < 1 || P < 1 || ld < n_rows) return fail(BN_ERR_BAD_ARG, "bad block shape");
+  int ndev = bn_device_count();
+  if (ndev <= 0) return fail(BN_ERR_NO_DEVICE, "no CUDA device available (libbn_b200 has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(BN_ERR_NO_DEVICE, "device %d out of range", device);
+  CU_TRY(cudaSetDevice(device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g_default_stream;
+  double *d_part = nullptr, *d_mean = nullptr;
+  CU_TRY(pool_alloc((void**)&d_part, (size_t)P * GRAM_MEAN_MAX_CHUNKS * sizeof(double)));
+  cudaError_t e = pool_alloc((void**)&d_mean, (size_t)P * sizeof(double));
+  if (e == cudaSuccess) {
+    gram_column_sums(dX, ld, n_rows, P, d_part, d_out_sum, d_mean, st);
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  pool_free(d_part); pool_free(d_mean);
+  if (e != cudaSuccess) return fail(BN_ERR_CUDA, "block column sums: %s", cudaGetErrorString(e));
+  return BN_OK;
+}
+
+extern "C" int bn_block_gram_device(const double* dX, int64_t ld, int n_rows, int P, const double* d_mean,
+                                    double* d_out_gram, int device, void* stream, float* ms) {
+  if (!dX || !d_mean || !d_out_gram) return fail(BN_ERR_BAD_ARG, "NULL argument");
+  if (n_rows < 1 || P < 2 || ld < n_rows) return fail(BN_ERR_BAD_ARG, "bad block shape");
+  int ndev = bn_device_count();
+  if (ndev <= 0) return fail(BN_ERR_NO_DEVICE, "no CUDA device available (libbn_b200 has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(BN_ERR_NO_DEVICE, "device %d out of range", device);
+  CU_TRY(cudaSetDevice(device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g_default_stream;
+  int n_sms = 148;
+  cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
+  const GramPlan pl = gram_plan(n_rows, P, n_sms);
+  double *dXc = nullptr, *d_partial = nullptr;
+  int* d_flag = nullptr;
+  cudaError_t e = pool_alloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_partial, (size_t)pl.workspace_bytes);
+  if (e == cudaSuccess) e = pool_alloc((void**)&d_flag, sizeof(int));
+  int rc = BN_OK;
+  if (e != cudaSuccess) rc = fail(BN_ERR_OOM, "block gram workspace allocation failed");
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (!rc) {
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+    const char* msg = gram_build(dX, ld, n_rows, P, dXc, pl.ld_centered, d_partial, pl, nullptr,
+                                 const_cast<double*>(d_mean), d_out_gram, P, nullptr, d_flag, st, nullptr, true);
+    if (msg) rc = fail(BN_ERR_CUDA, "gram_build: %s", msg);
+  }
+  if (!rc) {
+    cudaEventRecord(ev1, st);
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "block gram kernels: %s", cudaGetErrorString(e));
+  }
+  if (!rc) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ev0, ev1);
+    if (ms) *ms = t;
+    int flag = 0;
+    cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    if (flag) rc = fail(BN_ERR_CUDA, "gram_dmma_kernel: TMA pipeline timed out (flag %d)", flag);
+  }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  pool_free(dXc); pool_free(d_partial); pool_free(d_flag);
+  return rc;
+}
+
+extern "C" int bn_create_from_stats_device(int n_samples, int P, const double* d_mean, const double* d_centered,
+                                           const int* src, const int* tgt, int n_edges, const int* node_type,
+                                           int max_par, double phi, double omega, int device, bn_ctx** out) {
+  if (!d_mean || !d_centered) return fail(BN_ERR_BAD_ARG, "mean/centered_gram is NULL");
+  int rc = ctx_begin(n_samples, P, src, tgt, n_edges, node_type, max_par, phi, omega, device, out);
+  if (rc) { if (out && *out) { bn_destroy(*out); *out = nullptr; } return rc; }
+  bn_ctx* c = *out;
+  cudaError_t e = cudaMemcpyAsync(c->d_C, d_centered, (size_t)P * P * 8, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_mean, d_mean, (size_t)P * 8, cudaMemcpyDeviceToDevice, c->stream);
+  if (e == cudaSuccess) {
+    colsum_from_mean_kernel<<<(P + 127) / 128, 128, 0, c->stream>>>(c->d_mean, n_samples, P, c->d_colsum);
+    launch_diag(c->d_C, P, P, c->d_diag, c->stream);
+    c->launches += 2;
+    e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    rc = fail(BN_ERR_CUDA, "device sufficient statistics: %s", cudaGetErrorString(e));
     bn_destroy(c); *out = nullptr;
   }
   return rc;

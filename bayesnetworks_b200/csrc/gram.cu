@@ -320,17 +320,25 @@ GramPlan gram_plan(int n_samples, int P, int n_sms) {
   return pl;
 }
 
-const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, double* dXc, int64_t ld_centered,
-                       double* d_partial, const GramPlan& pl, double* d_colsum, double* d_mean,
-                       double* d_C, int64_t ldc, double* d_scratch_part, int* d_error_flag,
-                       cudaStream_t stream, int64_t* launches) {
-  // 1. means
+void gram_column_sums(const double* dX, int64_t ldx, int n_samples, int P, double* d_scratch_part,
+                      double* d_colsum, double* d_mean, cudaStream_t stream) {
   int chunks = (int)((n_samples + 65535) / 65536);
   if (chunks < 1) chunks = 1;
   if (chunks > GRAM_MEAN_MAX_CHUNKS) chunks = GRAM_MEAN_MAX_CHUNKS;
   column_sum_partial_kernel<<<dim3(P, chunks), 256, 0, stream>>>(dX, ldx, n_samples, chunks, d_scratch_part);
   column_mean_finish_kernel<<<(P + 127) / 128, 128, 0, stream>>>(d_scratch_part, chunks, P, n_samples,
                                                                   d_colsum, d_mean);
+}
+
+const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, double* dXc, int64_t ld_centered,
+                       double* d_partial, const GramPlan& pl, double* d_colsum, double* d_mean,
+                       double* d_C, int64_t ldc, double* d_scratch_part, int* d_error_flag,
+                       cudaStream_t stream, int64_t* launches, bool mean_given) {
+  // 1. means (skipped for a row block of a sharded matrix: the caller supplies the global means)
+  if (!mean_given) {
+    gram_column_sums(dX, ldx, n_samples, P, d_scratch_part, d_colsum, d_mean, stream);
+    if (launches) *launches += 2;
+  }
   // 2. centre
   int gx = (int)((ld_centered + 255) / 256);
   if (gx > 1024) gx = 1024;
@@ -357,7 +365,7 @@ const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, doub
   const int64_t total = (int64_t)P * P;
   gram_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_partial, pl.n_tiles, pl.n_pairs,
                                                                           pl.n_splits, P, d_C, ldc);
-  if (launches) *launches += 5;
+  if (launches) *launches += 3;
   return nullptr;
 }
 

@@ -19,11 +19,16 @@ struct GramPlan {
 
 GramPlan gram_plan(int n_samples, int P, int n_sms);
 
-// Enqueues means -> centring -> DMMA Gram -> reduction on `stream`.
+// column sums and means of an n_samples x P block (d_scratch_part: P * GRAM_MEAN_MAX_CHUNKS doubles)
+void gram_column_sums(const double* dX, int64_t ldx, int n_samples, int P, double* d_scratch_part,
+                      double* d_colsum, double* d_mean, cudaStream_t stream);
+
+// Enqueues means -> centring -> DMMA Gram -> reduction on `stream`.  With mean_given the
+// means stage is skipped and d_mean is read as supplied (row block of a sharded matrix).
 // Returns nullptr on success or a static error string.
 const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, double* dXc,
                        int64_t ld_centered, double* d_partial, const GramPlan& pl, double* d_colsum,
                        double* d_mean, double* d_C, int64_t ldc, double* d_scratch_part,
-                       int* d_error_flag, cudaStream_t stream, int64_t* launches);
+                       int* d_error_flag, cudaStream_t stream, int64_t* launches, bool mean_given = false);
 
 }  // namespace bn

@@ -7,6 +7,13 @@ blocks and counters (NCCL over NVLink on GPUs, gloo in the CPU tests).
 
 Chain identity is GLOBAL: chain c gets the same seeds and therefore the same trajectory
 whether the job runs on 1, 2, 4 or 8 GPUs (tests/test_dist_gloo.py, tests/test_gpu_*).
+
+The one place with a real exchange step is the sufficient statistics of a matrix whose
+sample axis is sharded over the GPUs (5,000 nodes x 1,000,000 samples = 40 GB): every rank
+builds the partial centred Gram of its row blocks and the parts are all-gathered and added
+in a FIXED block order (``sharded_sufficient_stats``), so the Gram -- and with it every
+trajectory -- is bit-identical for 1, 2, 4 or 8 GPUs; an all-reduce would add in a
+rank-count-dependent order.
 """
 from __future__ import annotations
 
@@ -103,3 +110,103 @@ def run_sharded(ctx, n_chains_total: int, n_iter: int, output: int, rank: int, w
     ints, gll, meta = pack_results(local, cap)
     gi, gg, gm = all_gather_chain_blocks(ints, gll, meta, n_chains_total, group=group, device=device)
     return unpack_results(gi, gg, gm), ms, local
+
+
+# ---------------------------------------------------------------------------
+# row-sharded sufficient statistics (SURVEY.md 8e)
+# ---------------------------------------------------------------------------
+N_ROW_BLOCKS = 8  # fixed logical partition of the sample axis, whatever the GPU count
+
+
+def row_blocks(n_samples: int, n_blocks: int = N_ROW_BLOCKS):
+    """[(first_row, n_rows)] of the logical row blocks (multiples of 16 rows, last takes the rest)."""
+    per = -(-n_samples // n_blocks)
+    per = -(-per // 16) * 16
+    out = []
+    for b in range(n_blocks):
+        lo = min(b * per, n_samples)
+        hi = min(lo + per, n_samples)
+        out.append((lo, hi - lo))
+    return out
+
+
+def blocks_of_rank(rank: int, world_size: int, n_blocks: int = N_ROW_BLOCKS):
+    """Logical blocks owned by ``rank`` (contiguous; world_size must divide n_blocks)."""
+    if n_blocks % world_size:
+        raise ValueError(f"world_size {world_size} must divide the {n_blocks} row blocks")
+    per = n_blocks // world_size
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def _ordered_sum(parts):
+    """parts[0] + parts[1] + ... in index order (elementwise, deterministic)."""
+    acc = parts[0].clone()
+    for b in range(1, parts.shape[0]):
+        acc += parts[b]
+    return acc
+
+
+def sharded_sufficient_stats(local_blocks, n_samples: int, n_nodes: int, rank: int, world_size: int,
+                             colsum_fn, gram_fn, device, group=None, n_blocks: int = N_ROW_BLOCKS):
+    """Global column means and centred Gram from row blocks spread over the ranks.
+
+    ``local_blocks``: this rank's blocks in logical order, whatever ``colsum_fn(block)`` ->
+    tensor [P] and ``gram_fn(block, mean)`` -> tensor [P, P] understand (device tensors of
+    shape (P, n_rows) on the GPU path; the CPU tests inject numpy-backed callables).
+    Every rank returns the same (mean [P], centred Gram [P, P]) -- bit-identical for any
+    world size because the parts are added in block order, not in rank-arrival order."""
+    import torch
+    import torch.distributed as dist
+
+    mine = blocks_of_rank(rank, world_size, n_blocks)
+    if len(local_blocks) != len(mine):
+        raise ValueError(f"rank {rank} owns {len(mine)} row blocks, got {len(local_blocks)}")
+
+    def gather(t):  # [n_local, ...] -> [n_blocks, ...] in logical block order
+        if world_size == 1:
+            return t
+        out = torch.empty((n_blocks,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
+
+    sums = torch.stack([colsum_fn(b) for b in local_blocks]).to(device)
+    mean = _ordered_sum(gather(sums)) / float(n_samples)
+    parts = torch.stack([gram_fn(b, mean) for b in local_blocks]).to(device)
+    gram = _ordered_sum(gather(parts))
+    return mean, gram
+
+
+def context_row_sharded(local_blocks, n_samples: int, n_nodes: int, graph_source, graph_target,
+                        graph_node_type, rank: int, world_size: int, device, max_par=50, phi=1.0,
+                        omega=6.9, group=None, n_blocks: int = N_ROW_BLOCKS):
+    """Context whose sufficient statistics come from row blocks sharded over the GPUs.
+
+    ``local_blocks``: CUDA float64 tensors of shape (n_nodes, n_rows_b) -- i.e. column-major
+    n_rows_b x n_nodes, contiguous -- for the logical blocks ``blocks_of_rank(rank, world_size)``.
+    Returns (Context, mean tensor, Gram tensor, ms spent in the Gram kernels of this rank)."""
+    import torch
+
+    from .api import Context, block_colsum_device, block_gram_device
+
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(device).cuda_stream
+    gram_ms = [0.0]
+
+    def colsum_fn(blk):
+        out = torch.empty(n_nodes, dtype=torch.float64, device=device)
+        block_colsum_device(blk.data_ptr(), blk.stride(0), blk.shape[1], n_nodes, out.data_ptr(), dev_index, stream)
+        return out
+
+    def gram_fn(blk, mean):
+        out = torch.empty((n_nodes, n_nodes), dtype=torch.float64, device=device)
+        gram_ms[0] += block_gram_device(blk.data_ptr(), blk.stride(0), blk.shape[1], n_nodes, mean.data_ptr(),
+                                        out.data_ptr(), dev_index, stream)
+        return out
+
+    mean, gram = sharded_sufficient_stats(local_blocks, n_samples, n_nodes, rank, world_size, colsum_fn, gram_fn,
+                                          device, group=group, n_blocks=n_blocks)
+    torch.cuda.synchronize(device)
+    ctx = Context.from_stats_device(n_samples, n_nodes, mean.data_ptr(), gram.data_ptr(), graph_source,
+                                    graph_target, graph_node_type, max_par=max_par, phi=phi, omega=omega,
+                                    device=dev_index)
+    return ctx, mean, gram, gram_ms[0]

@@ -81,6 +81,27 @@ int bn_create_from_stats(int n_samples, int n_nodes, const double* mean,
                          const int* node_type, int max_par, double phi, double omega,
                          int device, bn_ctx** out);
 
+/* Row-sharded sufficient statistics (the N axis of a matrix too large or too slow for one
+ * GPU, e.g. 5,000 x 1,000,000): a row block dX (n_rows x n_nodes, column-major, device
+ * memory) contributes its column sums, and -- once the caller has formed the GLOBAL means
+ * from the sums of all blocks -- its part of the centred cross-product matrix
+ *   out_gram[p1 + p2*P] = sum over the block's rows of (x_np1 - mean_p1)(x_np2 - mean_p2).
+ * The caller adds the parts of all blocks in a fixed block order (bit-identical for any
+ * number of GPUs; bayesnetworks_b200/dist.py does it with an NCCL all-gather) and hands the
+ * result to bn_create_from_stats_device.  All pointers are device pointers on `device`;
+ * stream NULL = the thread's default stream (bn_set_default_stream).  Replaces the same
+ * loop as bn_create: network::network, src/network.h:124-136. */
+int bn_block_colsum_device(const double* dX_colmajor, int64_t ld, int n_rows, int n_nodes,
+                           double* d_out_sum, int device, void* cuda_stream);
+int bn_block_gram_device(const double* dX_colmajor, int64_t ld, int n_rows, int n_nodes,
+                         const double* d_mean, double* d_out_gram, int device, void* cuda_stream,
+                         float* kernel_ms);
+int bn_create_from_stats_device(int n_samples, int n_nodes, const double* d_mean,
+                                const double* d_centered_gram,
+                                const int* edge_src_1b, const int* edge_tgt_1b, int n_edges,
+                                const int* node_type, int max_par, double phi, double omega,
+                                int device, bn_ctx** out);
+
 void bn_destroy(bn_ctx* ctx);
 
 /* Scratch device buffers are pooled per device between calls (cudaMalloc/cudaFree cost more

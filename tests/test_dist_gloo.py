@@ -71,3 +71,74 @@ def test_all_gather_world2_gloo(tmp_path, n_chains):
     res = unpack_results(want_i, want_g, want_m)
     assert len(res) == n_chains and res[3]["total_edges"] == 3
     assert np.array_equal(res[2]["trace"]["globalLL"], FakeResult(2, cap).trace["globalLL"])
+
+
+# ---------------------------------------------------------------------------
+# row-sharded sufficient statistics: fixed-order reduction over gloo
+# ---------------------------------------------------------------------------
+def _numpy_block_fns():
+    import torch as _t
+
+    def colsum_fn(blk):  # blk: (P, n_rows) float64 numpy
+        return _t.from_numpy(blk.sum(axis=1))
+
+    def gram_fn(blk, mean):
+        xc = blk - mean.numpy()[:, None]
+        return _t.from_numpy(xc @ xc.T)
+
+    return colsum_fn, gram_fn
+
+
+def _stats_data(n=1000, p=13):
+    rng = np.random.default_rng(7)
+    return np.ascontiguousarray((rng.standard_normal((p, n)) * 3.0 + rng.uniform(-50, 50, (p, 1))))
+
+
+def _stats_worker(rank, world, port, out_dir):
+    from bayesnetworks_b200.dist import blocks_of_rank, row_blocks, sharded_sufficient_stats
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X = _stats_data()
+    p, n = X.shape
+    rb = row_blocks(n)
+    local = [np.ascontiguousarray(X[:, rb[b][0]:rb[b][0] + rb[b][1]]) for b in blocks_of_rank(rank, world)]
+    colsum_fn, gram_fn = _numpy_block_fns()
+    mean, gram = sharded_sufficient_stats(local, n, p, rank, world, colsum_fn, gram_fn, torch.device("cpu"))
+    np.savez(os.path.join(out_dir, f"stats{rank}.npz"), mean=mean.numpy(), gram=gram.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_blocks_partition():
+    from bayesnetworks_b200.dist import blocks_of_rank, row_blocks
+    for n in (1000, 1_000_000, 17, 128, 100_003):
+        rb = row_blocks(n)
+        assert len(rb) == 8 and sum(c for _, c in rb) == n
+        pos = 0
+        for lo, cnt in rb:
+            assert lo == pos and (lo % 16 == 0 or cnt == 0)
+            pos += cnt
+    for w in (1, 2, 4, 8):
+        assert sorted(b for r in range(w) for b in blocks_of_rank(r, w)) == list(range(8))
+    with pytest.raises(ValueError):
+        blocks_of_rank(0, 3)
+
+
+def test_sharded_stats_world2_gloo_matches_single_process(tmp_path):
+    """The Gram of the row-sharded path does not depend on the number of ranks (bit-identical)."""
+    from bayesnetworks_b200.dist import row_blocks, sharded_sufficient_stats
+    world = 2
+    mp.spawn(_stats_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    X = _stats_data()
+    p, n = X.shape
+    rb = row_blocks(n)
+    blocks = [np.ascontiguousarray(X[:, lo:lo + cnt]) for lo, cnt in rb]
+    colsum_fn, gram_fn = _numpy_block_fns()
+    mean1, gram1 = sharded_sufficient_stats(blocks, n, p, 0, 1, colsum_fn, gram_fn, torch.device("cpu"))
+    for r in range(world):
+        z = np.load(tmp_path / f"stats{r}.npz")
+        assert np.array_equal(z["mean"], mean1.numpy()) and np.array_equal(z["gram"], gram1.numpy())
+    # and it is the centred cross-product matrix
+    xc = X - X.mean(axis=1, keepdims=True)
+    assert np.allclose(gram1.numpy(), xc @ xc.T, rtol=1e-12, atol=1e-9)
+    assert np.allclose(mean1.numpy(), X.mean(axis=1), rtol=1e-14)

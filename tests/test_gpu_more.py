@@ -95,6 +95,39 @@ def test_constructors_agree(dataset):
     assert np.allclose(ra.trace["globalLL"], rc.trace["globalLL"], rtol=1e-10, atol=1e-7)
 
 
+def test_row_sharded_statistics_single_gpu(dataset):
+    """Row-sharded Gram (8 logical row blocks + fixed-order sum) on one GPU: the
+    statistics agree with the one-shot build to rounding and the chain is the same."""
+    import torch
+    from bayesnetworks_b200 import Context
+    from bayesnetworks_b200.dist import context_row_sharded, row_blocks
+    X, src, tgt, nt = dataset["X"], dataset["source"], dataset["target"], dataset["node_type"]
+    N, P = X.shape
+    dev = torch.device("cuda", 0)
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)  # (P, N)
+    blocks = [Xd[:, lo:lo + cnt].contiguous() for lo, cnt in row_blocks(N)]
+    ctx, mean, gram, ms = context_row_sharded(blocks, N, P, src, tgt, nt, 0, 1, dev, max_par=8)
+    with ctx:
+        ss = ctx.stats()
+        rs = ctx.run(n_iter=3000, output=10, rng="wh")[0][0]
+    with Context.from_device(Xd.data_ptr(), N, N, P, src, tgt, nt, max_par=8) as b:
+        sb = b.stats()
+        rb = b.run(n_iter=3000, output=10, rng="wh")[0][0]
+    assert ms > 0
+    assert np.allclose(ss[2], sb[2], rtol=1e-13, atol=1e-13)               # means
+    assert np.allclose(ss[3], sb[3], rtol=1e-11, atol=1e-8)                # centred Gram
+    assert np.allclose(ss[1], sb[1], rtol=1e-11, atol=1e-8)                # sumXX
+    mean_ref, C_ref = centered_stats(X)
+    assert np.allclose(gram.cpu().numpy(), C_ref, rtol=1e-11, atol=1e-8)
+    for k in INT_COLS:
+        assert np.array_equal(rs.trace[k], rb.trace[k]), k
+    assert np.allclose(rs.trace["globalLL"], rb.trace["globalLL"], rtol=1e-10, atol=1e-7)
+    # a second build gives the same bits (no atomics, fixed order)
+    ctx2, mean2, gram2, _ = context_row_sharded(blocks, N, P, src, tgt, nt, 0, 1, dev, max_par=8)
+    ctx2.close()
+    assert torch.equal(gram, gram2) and torch.equal(mean, mean2)
+
+
 def test_odd_sample_count_and_ragged_tiles(oracle):
     """N not a multiple of 16 (TMA zero-fill of the sample tail) and P not a multiple of 128."""
     from bayesnetworks_b200 import Context

@@ -24,6 +24,27 @@ with Context.from_data(z["X"], z["source"], z["target"], z["node_type"], max_par
             ok &= allres[c]["uniforms"] == truth[c].uniforms
         g = np.load(os.path.join(os.path.dirname(__file__), "..", "golden", "golden_ref.npz"))
         ok &= bool(np.array_equal(allres[0]["trace"]["ChangedNode"], g["cfg2_ChangedNode"][:n_iter // output]))
+# row-sharded Gram: every rank must end with the bits a single GPU produces from the same 8 blocks
+from bayesnetworks_b200.dist import blocks_of_rank, context_row_sharded, row_blocks
+dev = torch.device("cuda", local)
+Xd = torch.from_numpy(np.ascontiguousarray(z["X"].T)).to(dev)
+N, P = z["X"].shape
+rb = row_blocks(N)
+if 8 % world == 0:
+    mine = [Xd[:, rb[b][0]:rb[b][0] + rb[b][1]].contiguous() for b in blocks_of_rank(rank, world)]
+    cs, mean_s, gram_s, _ = context_row_sharded(mine, N, P, z["source"], z["target"], z["node_type"], rank, world,
+                                                dev, max_par=8)
+    r_sh = cs.run(n_iter=2000, output=100, rng="wh")[0][0]
+    cs.close()
+    if rank == 0:
+        allb = [Xd[:, lo:lo + cnt].contiguous() for lo, cnt in rb]
+        import torch.distributed as _d
+        c1, mean_1, gram_1, _ = context_row_sharded(allb, N, P, z["source"], z["target"], z["node_type"], 0, 1, dev,
+                                                    max_par=8)
+        r_1 = c1.run(n_iter=2000, output=100, rng="wh")[0][0]
+        c1.close()
+        ok &= bool(torch.equal(gram_s, gram_1)) and bool(torch.equal(mean_s, mean_1))
+        ok &= bool(np.array_equal(r_sh.trace["globalLL"], r_1.trace["globalLL"]))
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
