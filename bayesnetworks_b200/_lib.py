@@ -62,7 +62,8 @@ class RunArgs(C.Structure):
     _fields_ = [("n_chains", C.c_int), ("rng_kind", C.c_int), ("seeds", _ip), ("replay", _dp),
                 ("replay_len", C.c_int64), ("initial_network", C.c_int), ("drop", C.c_int),
                 ("n_iter", C.c_int), ("output_every", C.c_int), ("device_outputs", C.c_int),
-                ("moves_capacity", C.c_int), ("n_moves", _ip), ("moves", _ip), ("edge_freq", _ip)]
+                ("moves_capacity", C.c_int), ("n_moves", _ip), ("moves", _ip), ("edge_freq", _ip),
+                ("npar_freq", _ip)]
 
 
 _lib = None

@@ -44,6 +44,7 @@ class ChainResult:
     final_npar: np.ndarray
     accepted_moves: Optional[np.ndarray] = None  # rows (iter, movetype, child, parent)
     edge_freq: Optional[np.ndarray] = None       # [child, parent] counts (posterior tabulation)
+    npar_freq: Optional[np.ndarray] = None       # [node, k] iterations spent with k parents
 
     def edges(self):
         """(parent, child) pairs, 0-based, per-child list order."""
@@ -250,10 +251,12 @@ class Context:
             args.moves_capacity = moves.shape[1]
             args.moves = moves.ctypes.data_as(_lib._ip)
             args.n_moves = n_moves.ctypes.data_as(_lib._ip)
-        freq = None
+        freq = nfreq = None
         if tabulate:
             freq = np.zeros((n_chains, p, p), dtype=np.int32)
             args.edge_freq = freq.ctypes.data_as(_lib._ip)
+            nfreq = np.zeros((n_chains, p, mp + 1), dtype=np.int32)
+            args.npar_freq = nfreq.ctypes.data_as(_lib._ip)
         fpar = np.full((n_chains, p, mp), -1, dtype=np.int32)
         fnpar = np.zeros((n_chains, p), dtype=np.int32)
         stats = (_lib.ChainStats * n_chains)()
@@ -282,7 +285,8 @@ class Context:
                 final_parents=fpar[ch],
                 final_npar=fnpar[ch],
                 accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])],
-                edge_freq=None if freq is None else freq[ch]))
+                edge_freq=None if freq is None else freq[ch],
+                npar_freq=None if nfreq is None else nfreq[ch]))
         return out, float(ms.value)
 
 

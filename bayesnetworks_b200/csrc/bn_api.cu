@@ -693,6 +693,12 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
     else CU_TRY(buf.alloc(&w.edge_freq, (size_t)(nc * P * P)));
     CU_TRY(cudaMemsetAsync(w.edge_freq, 0, (size_t)(nc * P * P) * 4, c->stream));
   }
+  if (a->npar_freq) {
+    if (dev_out) w.npar_freq = a->npar_freq;
+    else CU_TRY(buf.alloc(&w.npar_freq, (size_t)(nc * P * (MP + 1))));
+    CU_TRY(buf.alloc(&w.npar_since, (size_t)(nc * P)));
+    CU_TRY(cudaMemsetAsync(w.npar_freq, 0, (size_t)(nc * P * (MP + 1)) * 4, c->stream));
+  }
 
   // uniform streams
   ChainRngArgs ra;
@@ -802,6 +808,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
     CU_TRY(cudaMemcpy(trace->fp, w.t_fp, n * 4, cudaMemcpyDeviceToHost));
     if (mcap) CU_TRY(cudaMemcpy(a->moves, w.moves, (size_t)nc * mcap * 16, cudaMemcpyDeviceToHost));
     if (a->edge_freq) CU_TRY(cudaMemcpy(a->edge_freq, w.edge_freq, (size_t)(nc * P * P) * 4, cudaMemcpyDeviceToHost));
+    if (a->npar_freq) CU_TRY(cudaMemcpy(a->npar_freq, w.npar_freq, (size_t)(nc * P * (MP + 1)) * 4, cudaMemcpyDeviceToHost));
   }
   const cudaMemcpyKind fin_kind = dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (final_parents) CU_TRY(cudaMemcpy(final_parents, w.par, (size_t)(nc * P * MP) * 4, fin_kind));

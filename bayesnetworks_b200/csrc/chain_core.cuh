@@ -72,6 +72,8 @@ struct ChainMem {  // per-chain global memory
   int* t_add; int* t_del; int* t_fn; int* t_fp;
   int* moves;          // [moves_capacity][4]
   int* edge_freq;      // [parent + child*P] or null
+  int* npar_freq;      // [P][max_par + 1] iterations node p spent with k parents, or null
+  int* npar_since;     // [P] first counted iteration of the node's current parent count
 };
 
 struct ChainScalars {  // lives in registers (warp-uniform)
@@ -594,6 +596,8 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
     m.par[i] = (p.initial_network == 0 && (int)(i % MP) < p.prior_npar[i / MP]) ? p.prior_par[i] : -1;
     m.born[i] = p.drop;  // edges of the start graph are counted from iteration `drop`
   }
+  if (m.npar_freq)
+    for (int i = l; i < P; i += Warp::NL) m.npar_since[i] = p.drop;
   for (int i = l; i < P; i += Warp::NL) m.npar[i] = (p.initial_network == 0) ? p.prior_npar[i] : 0;
   for (int w = l; w < p.W; w += Warp::NL) m.haspar[w] = 0u;
   Warp::sync();
@@ -1119,6 +1123,13 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
   const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
   Warp::sync();
+  if (l == 0 && m.npar_freq) {
+    // freqNpar[p][Npar[p]]++ of Tabulate() (Bayes-networks/main.cpp:291): the old count held
+    // from npar_since[c] up to this iteration
+    const int64_t cnt = first_counted - m.npar_since[c];
+    if (cnt > 0) m.npar_freq[(int64_t)c * (MP + 1) + k] += (int)cnt;
+    m.npar_since[c] = (int)first_counted;
+  }
   if (type == 1) {
     if (l == 0) {
       pc[k] = j; bc[k] = (int)first_counted; m.npar[c] = k + 1;
@@ -1432,7 +1443,14 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
       s.win = w > WIN ? WIN : w;
     }
   }
-  // flush the posterior tabulation of the surviving edges
+  // flush the posterior tabulation of the surviving edges / parent counts
+  if (m.npar_freq) {
+    Warp::sync();
+    for (int c = l; c < p.P; c += Warp::NL) {
+      const int64_t cnt = (int64_t)p.n_iter - m.npar_since[c];
+      if (cnt > 0) m.npar_freq[(int64_t)c * (p.max_par + 1) + m.npar[c]] += (int)cnt;
+    }
+  }
   if (m.edge_freq) {
     Warp::sync();
     for (int c = l; c < p.P; c += Warp::NL) {

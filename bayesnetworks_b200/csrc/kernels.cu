@@ -54,6 +54,8 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
   m.t_fn = w.t_fn + ch * cap; m.t_fp = w.t_fp + ch * cap;
   m.moves = w.moves ? w.moves + (int64_t)ch * p.moves_capacity * 4 : nullptr;
   m.edge_freq = w.edge_freq ? w.edge_freq + ch * P * P : nullptr;
+  m.npar_freq = w.npar_freq ? w.npar_freq + ch * P * (MP + 1) : nullptr;
+  m.npar_since = w.npar_since ? w.npar_since + ch * P : nullptr;
   m.helper = helper_cmd;
 
   RngStream rng;

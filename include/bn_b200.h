@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BN_B200_ABI_VERSION 1
+#define BN_B200_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------- */
 enum {
@@ -212,6 +212,9 @@ typedef struct bn_run_args {
      edge_freq[chain][parent + child*P] += 1 for every edge of the kept graph after each
      iteration i with i+1 > drop */
   int* edge_freq;
+  /* freqNpar of the same Tabulate(), main.cpp:291 (optional, may be NULL; ABI version >= 2):
+     npar_freq[chain][node*(max_par+1) + k] = counted iterations the node spent with k parents */
+  int* npar_freq;
 } bn_run_args;
 
 /* final_parents: [n_chains][P][max_par] (-1 padded), final_n_par: [n_chains][P]; may be NULL.

@@ -19,7 +19,7 @@ extern "C" int emu_run_chain(
     int rng_kind, const int* seeds, const unsigned int* mt_state, const double* replay,
     long replay_len, int capacity,
     int* t_iter, int* t_changed, int* t_movetype, double* t_gll, int* t_add, int* t_del,
-    int* t_fn, int* t_fp, int moves_capacity, int* moves, int* edge_freq,
+    int* t_fn, int* t_fp, int moves_capacity, int* moves, int* edge_freq, int* npar_freq,
     int* final_par, int* final_npar, long* out_counters /*[12]*/) {
   ChainParams p;
   p.P = P; p.max_par = max_par; p.W = (P + 31) / 32; p.Ws = (p.W + 3) / 4 * 4; p.n_samples = n_samples;
@@ -43,6 +43,8 @@ extern "C" int emu_run_chain(
   m.t_iter = t_iter; m.t_changed = t_changed; m.t_movetype = t_movetype; m.t_gll = t_gll;
   m.t_add = t_add; m.t_del = t_del; m.t_fn = t_fn; m.t_fp = t_fp;
   m.moves = moves; m.edge_freq = edge_freq;
+  std::vector<int> npar_since(P);
+  m.npar_freq = npar_freq; m.npar_since = npar_since.data();
 
   std::vector<double> ubuf(RNG_CAP);
   RngStream rng;

@@ -128,6 +128,21 @@ def test_row_sharded_statistics_single_gpu(dataset):
     assert torch.equal(gram, gram2) and torch.equal(mean, mean2)
 
 
+def test_long_rejection_loops_vs_oracle(oracle):
+    """Iterations that consume hundreds of uniforms (296 of 300 nodes are sources): position
+    records overflow their 255-uniform count and the sequential window path takes over."""
+    from bayesnetworks_b200 import Context
+    from oracle.oracle import RNG_WH
+    from test_host_logic import _mostly_sources_case
+    X, src, tgt, nt = _mostly_sources_case()
+    n_iter = 6000
+    ref = oracle.mcmc(X, src, tgt, nt, max_par=8, phi=1.0, omega=1.0, n_iter=n_iter, output=5,
+                      rng_kind=RNG_WH, seeds=(321, 654, 987))
+    with Context.from_data(X, src, tgt, nt, max_par=8, omega=1.0) as ctx:
+        r = ctx.run(n_iter=n_iter, output=5, rng="wh", seeds=(321, 654, 987), log_moves=True)[0][0]
+    _same_trace(r, ref, X.shape[0])
+
+
 def test_odd_sample_count_and_ragged_tiles(oracle):
     """N not a multiple of 16 (TMA zero-fill of the sample tail) and P not a multiple of 128."""
     from bayesnetworks_b200 import Context
@@ -156,15 +171,19 @@ def test_replay_stream_and_tabulation(dataset, oracle):
     # i >= drop, every edge of the kept graph counts once
     P = X.shape[1]
     cur, freq = set(), np.zeros((P, P), np.int64)
+    npar, nfreq = np.zeros(P, np.int64), np.zeros((P, 9), np.int64)
     mv = {int(m[0]): m for m in r.accepted_moves}
     for it in range(5000):
         if it in mv:
             _, typ, c, j = mv[it]
             (cur.add if typ == 1 else cur.discard)((int(j), int(c)))
+            npar[c] += 1 if typ == 1 else -1
         if it >= 100:
             for (j, c) in cur:
                 freq[c, j] += 1
+            nfreq[np.arange(P), npar] += 1   # freqNpar[p][Npar[p]]++, main.cpp:291
     assert np.array_equal(r.edge_freq, freq)
+    assert np.array_equal(r.npar_freq, nfreq)
 
 
 def test_error_behaviour(dataset):

@@ -139,6 +139,7 @@ def _emu_run(lib, dataset, max_par, n_iter, output, kind, seeds, init=2, drop=0,
     gll = np.zeros(cap)
     moves = np.zeros((n_iter, 4), np.int32)
     freq = np.zeros((P, P), np.int32)
+    nfreq = np.zeros((P, max_par + 1), np.int32)
     fpar = np.zeros((P, max_par), np.int32)
     fnpar = np.zeros(P, np.int32)
     cnt = np.zeros(12, np.int64)
@@ -155,12 +156,12 @@ def _emu_run(lib, dataset, max_par, n_iter, output, kind, seeds, init=2, drop=0,
         ti[0].ctypes.data_as(ip), ti[1].ctypes.data_as(ip), ti[2].ctypes.data_as(ip),
         gll.ctypes.data_as(dp), ti[3].ctypes.data_as(ip), ti[4].ctypes.data_as(ip),
         ti[5].ctypes.data_as(ip), ti[6].ctypes.data_as(ip), n_iter, moves.ctypes.data_as(ip),
-        freq.ctypes.data_as(ip), fpar.ctypes.data_as(ip), fnpar.ctypes.data_as(ip),
+        freq.ctypes.data_as(ip), nfreq.ctypes.data_as(ip), fpar.ctypes.data_as(ip), fnpar.ctypes.data_as(ip),
         cnt.ctypes.data_as(C.POINTER(C.c_long)))
     n = int(cnt[8])
     out = dict(zip(INT_COLS, [ti[0][:n], ti[1][:n], ti[2][:n], ti[3][:n], ti[4][:n], ti[5][:n], ti[6][:n]]))
     out.update(rc=rc, globalLL=gll[:n], moves=moves[:int(cnt[9])], cnt=cnt, fpar=fpar, fnpar=fnpar,
-               freq=freq)
+               freq=freq, nfreq=nfreq)
     return out
 
 
@@ -187,13 +188,17 @@ def test_chain_core_every_iteration_and_tabulation(emu_lib, dataset, golden):
     # posterior tabulation (Bayes-networks/main.cpp:289-297): replay the accepted moves
     P = 81
     cur, freq, mv = set(), np.zeros((P, P), np.int64), {int(m[0]): m for m in r["moves"]}
+    npar, nfreq = np.zeros(P, np.int64), np.zeros((P, 9), np.int64)
     for it in range(4000):
         if it in mv:
             _, typ, c, j = mv[it]
             (cur.add if typ == 1 else cur.discard)((int(j), int(c)))
+            npar[c] += 1 if typ == 1 else -1
         for (j, c) in cur:
             freq[c, j] += 1
+        nfreq[np.arange(P), npar] += 1   # freqNpar[p][Npar[p]]++, main.cpp:291
     assert np.array_equal(r["freq"], freq)
+    assert np.array_equal(r["nfreq"], nfreq)
     r0 = _emu_run(emu_lib, dataset, 8, 2000, 1, 1, (99,), init=0)
     for k in INT_COLS:
         assert np.array_equal(r0[k], golden[f"every_init0_{k}"]), k
@@ -264,7 +269,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.bn_abi_version() == 1
+    assert L.bn_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -314,3 +319,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), f
+
+
+def _mostly_sources_case():
+    """300 nodes of which 296 are sources: the child draw of an addition is rejected with
+    probability 296/300, so iterations that need hundreds of uniforms are common -- more than
+    a position record can count (255), which sends them through the sequential window path."""
+    rng = np.random.default_rng(11)
+    P, N = 300, 400
+    X = np.asfortranarray(rng.standard_normal((N, P)))
+    for c, ps in ((296, (0, 1)), (297, (2, 296)), (298, (3, 4, 5)), (299, (297, 6))):
+        for q in ps:
+            X[:, c] += 0.7 * X[:, q]
+    nt = np.ones(P, dtype=np.int32)
+    nt[296:] = 0
+    src = np.array([1, 2, 3, 297, 4, 5], dtype=np.int32)
+    tgt = np.array([297, 297, 298, 298, 299, 299], dtype=np.int32)
+    return X, src, tgt, nt
+
+
+def test_chain_core_long_rejection_loops_vs_oracle(emu_lib, oracle):
+    from oracle.oracle import RNG_WH
+    X, src, tgt, nt = _mostly_sources_case()
+    n_iter = 6000
+    ref = oracle.mcmc(X, src, tgt, nt, max_par=8, phi=1.0, omega=1.0, n_iter=n_iter, output=5,
+                      rng_kind=RNG_WH, seeds=(321, 654, 987))
+    ds = dict(X=X, source=src, target=tgt, node_type=nt)
+    r = _emu_run(emu_lib, ds, 8, n_iter, 5, 0, (321, 654, 987), omega=1.0)
+    assert r["rc"] == 0
+    for k in INT_COLS:
+        assert np.array_equal(r[k], getattr(ref, k)), k
+    assert int(r["cnt"][0]) == ref.uniforms
+    assert ref.uniforms > 30 * n_iter  # ~75 child draws per addition; 3.5% of them need more than 255
