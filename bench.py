@@ -282,11 +282,20 @@ def run_ours(a):
     # dominant kernel of the step = the persistent chain kernel (one launch per step per GPU)
     per_gpu_bytes = alg_bytes / world
     achieved = per_gpu_bytes / (chain_ms * 1e-3) / 1e9
+    # DRAM bytes of one launch from the committed ncu --set full capture (null if absent)
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "r01_chain_traffic.json")
+    if os.path.exists(tr_path):
+        tr = json.load(open(tr_path))
+        traffic = float(tr["dram_bytes_read"]) + float(tr["dram_bytes_write"])
     roofline = {"bound": "hbm", "kernel": "chain_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": chain_ms, "share_of_step": chain_ms / ms_per_step,
-                "note": "latency-bound sequential chains: algorithmic gather bytes = sum over scored "
-                        "proposals of 8*(k'+1)(k'+2)/2+8 (SURVEY.md 8d); the Gram (8 MB) is L2 resident"}
+                "note": "latency-bound sequential chains (dependent instruction stream, see "
+                        "profiles/r01_chain_kernel.md): algorithmic gather bytes = sum over scored proposals of "
+                        "8*(k'+1)(k'+2)/2+8 (SURVEY.md 8d); the Gram (8 MB) is L2 resident, so DRAM traffic "
+                        "(`traffic`, bytes per launch, ncu) is far BELOW the algorithmic bytes; the HBM-bound "
+                        "scoring kernel of this path is kernels.sweep"}
 
     line = {"metric": METRIC, "value": proposals / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
