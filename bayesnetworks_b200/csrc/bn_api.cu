@@ -672,6 +672,8 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   CU_TRY(buf.alloc(&w.haspar, (size_t)(nc * W)));
   CU_TRY(buf.alloc(&w.hp_list, (size_t)(nc * P)));
   CU_TRY(buf.alloc(&w.scratch, (size_t)nc * w.scratch_n));
+  CU_TRY(buf.alloc(&w.dscore, (size_t)(nc * P * MP)));
+  CU_TRY(cudaMemsetAsync(w.dscore, 0xff, (size_t)(nc * P * MP) * sizeof(double), c->stream));  // NaN = unknown
   const bool dev_out = a->device_outputs != 0;
   if (dev_out) {
     w.t_iter = trace->iter; w.t_changed = trace->changed_node; w.t_movetype = trace->movetype;

@@ -72,6 +72,7 @@ struct ChainMem {  // per-chain global memory
   int* t_add; int* t_del; int* t_fn; int* t_fp;
   int* moves;          // [moves_capacity][4]
   int* edge_freq;      // [parent + child*P] or null
+  double* dscore;      // [P][max_par] cache of score(c | parents without slot e), NaN = unknown; or null
   int* npar_freq;      // [P][max_par + 1] iterations node p spent with k parents, or null
   int* npar_since;     // [P] first counted iteration of the node's current parent count
 };
@@ -926,6 +927,14 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   ws.t_rec[slot] = rec;
 }
 
+BN_HD double nan_sentinel() {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(-1ll);
+#else
+  return NAN;
+#endif
+}
+
 template <int KMAX>
 BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
                         WindowSlots& ws, int slot) {
@@ -933,8 +942,21 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
   const int rec = ws.t_rec[slot];
   if (rec & REC_OVF) return;
   int kk = 0, npd = 0;
-  ws.t_score[slot] = score_proposal<KMAX>(p, m, (rec & REC_TYPE) ? 2 : 1, ws.t_c[slot], ws.t_j[slot],
-                                          ws.t_e[slot], &kk, &npd);
+  double sc;
+  // the score of a deletion is a function of (child, slot) until the child's parents change:
+  // it is kept in a per-chain table (L2), which takes half of the records off the sub-Gram
+  // gather -- the throughput limit of this phase (one L1TEX wavefront per gathered entry)
+  double* cache = (m.dscore && (rec & REC_TYPE)) ? m.dscore + (int64_t)ws.t_c[slot] * p.max_par + ws.t_e[slot] : nullptr;
+  const double cached = cache ? ld_shared_ro(cache) : nan_sentinel();
+  if (cached == cached) {
+    sc = cached;
+    kk = m.npar[ws.t_c[slot]] - 1;
+    npd = (sc == -INFINITY) ? 1 : 0;
+  } else {
+    sc = score_proposal<KMAX>(p, m, (rec & REC_TYPE) ? 2 : 1, ws.t_c[slot], ws.t_j[slot], ws.t_e[slot], &kk, &npd);
+    if (cache) *cache = sc;  // (duplicates within a round store the same value)
+  }
+  ws.t_score[slot] = sc;
   ws.t_rec[slot] = rec | (npd ? REC_NPD : 0) | (kk << REC_KK_SHIFT);
   decide_record(p, m, rc, ubuf, ws, slot);
 }
@@ -1115,12 +1137,11 @@ BN_HD void write_row(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t
 }
 
 BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it, int type, int c,
-                           int j, int del, double new_score) {
+                           int j, int del, double new_score, int ag) {
   const int MP = p.max_par, l = Warp::lane();
   int* pc = m.par + (int64_t)c * MP;
   int* bc = m.born + (int64_t)c * MP;
   const int k = m.npar[c];
-  const int ag = p.sim_edge[(int64_t)j + (int64_t)c * p.P] ? 1 : 0;
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
   Warp::sync();
   if (l == 0 && m.npar_freq) {
@@ -1165,6 +1186,8 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     Warp::sync();
     anc_after_delete(p, m, c);
   }
+  if (m.dscore)  // the deletion scores of c are no longer valid
+    for (int e = l; e < MP; e += Warp::NL) m.dscore[(int64_t)c * MP + e] = nan_sentinel();
   if (s.n_moves < p.moves_capacity) {
     if (l == 0) {
       int* mv = m.moves + (int64_t)s.n_moves * 4;
@@ -1178,7 +1201,8 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
 
 BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
                       const WindowSlots& ws, int i) {
-  apply_move_vals(p, m, s, it, ws.type[i], ws.child[i], ws.parent[i], ws.pos[i], ws.new_score[i]);
+  const int ag = p.sim_edge[(int64_t)ws.parent[i] + (int64_t)ws.child[i] * p.P] ? 1 : 0;
+  apply_move_vals(p, m, s, it, ws.type[i], ws.child[i], ws.parent[i], ws.pos[i], ws.new_score[i], ag);
 }
 
 // Commit slots [0, ncommit): all but possibly the last are rejections/invalid.
@@ -1316,7 +1340,8 @@ BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const 
   if (acc) {
     const int c = ws.t_c[k_acc], a_type = (ws.t_rec[k_acc] & REC_TYPE) ? 2 : 1;
     const long long ta = cycle_now();
-    apply_move_vals(p, m, s, s.iter + last, a_type, c, ws.t_j[k_acc], ws.t_e[k_acc], ws.t_score[k_acc]);
+    apply_move_vals(p, m, s, s.iter + last, a_type, c, ws.t_j[k_acc], ws.t_e[k_acc], ws.t_score[k_acc],
+                    (ws.t_rec[k_acc] & REC_AG) ? 1 : 0);
     dt = cycle_now() - ta;
     s.cyc[a_type == 1 ? 4 : 5] += dt;
     if (m_log & accbit)

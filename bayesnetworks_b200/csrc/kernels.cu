@@ -56,6 +56,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
   m.edge_freq = w.edge_freq ? w.edge_freq + ch * P * P : nullptr;
   m.npar_freq = w.npar_freq ? w.npar_freq + ch * P * (MP + 1) : nullptr;
   m.npar_since = w.npar_since ? w.npar_since + ch * P : nullptr;
+  m.dscore = w.dscore ? w.dscore + ch * P * MP : nullptr;
   m.helper = helper_cmd;
 
   RngStream rng;

@@ -15,6 +15,7 @@ struct ChainWorkspace {  // arrays over all chains of a run (device memory)
   int* t_iter; int* t_changed; int* t_movetype; double* t_gll;
   int* t_add; int* t_del; int* t_fn; int* t_fp;
   int* moves; int* edge_freq; int* npar_freq; int* npar_since;
+  double* dscore;                      // [nc][P][max_par] deletion-score cache (all-ones = unknown)
 };
 
 // Which per-chain arrays live in dynamic shared memory (byte offset, -1 = global memory).

@@ -45,6 +45,8 @@ extern "C" int emu_run_chain(
   m.moves = moves; m.edge_freq = edge_freq;
   std::vector<int> npar_since(P);
   m.npar_freq = npar_freq; m.npar_since = npar_since.data();
+  std::vector<double> dscore((size_t)P * max_par, NAN);
+  m.dscore = dscore.data();
 
   std::vector<double> ubuf(RNG_CAP);
   RngStream rng;
