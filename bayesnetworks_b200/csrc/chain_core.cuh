@@ -626,10 +626,11 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
     const int k = m.npar[c];
     int npd = 0;
     if constexpr (KMAX <= 8) {
-      int S[KMAX];
+      Parents8 S;
 #pragma unroll
-      for (int e = 0; e < KMAX; e++) S[e] = (e < k) ? m.par[(int64_t)c * MP + e] : c;
-      m.base[c] = score_set_small<KMAX>(p.C, p.ldc, c, S, k, p.n_samples, &npd);
+      for (int e = 0; e < 8; e++) S.s[e] = (e < k) ? m.par[(int64_t)c * MP + e] : c;
+      m.base[c] = score_set8(p.C, p.ldc, c, S, k, p.n_samples);
+      npd = (m.base[c] == -INFINITY) ? 1 : 0;
     } else {
       double L[KMAX * (KMAX + 1) / 2], z[KMAX];
       int S[KMAX];
@@ -751,20 +752,21 @@ BN_HD double score_proposal(const ChainParams& p, const ChainMem& m, int type, i
   int kk = 0;
   double nw;
   if constexpr (KMAX <= 8) {
-    int S[KMAX];
+    Parents8 S;
     if (type == 1) {
       kk = k + 1;
 #pragma unroll
-      for (int e = 0; e < KMAX; e++) S[e] = (e < k) ? pc[e] : j;
+      for (int e = 0; e < 8; e++) S.s[e] = (e < k) ? pc[e] : j;
     } else {
       kk = k - 1;
 #pragma unroll
-      for (int e = 0; e < KMAX; e++) {
+      for (int e = 0; e < 8; e++) {
         const int src = e + (e >= del ? 1 : 0);
-        S[e] = (src < k) ? pc[src] : c;
+        S.s[e] = (src < k) ? pc[src] : c;
       }
     }
-    nw = score_set_small<KMAX>(p.C, p.ldc, c, S, kk, p.n_samples, npd);
+    nw = score_set8(p.C, p.ldc, c, S, kk, p.n_samples);
+    *npd = (nw == -INFINITY) ? 1 : 0;
   } else {
     double L[KMAX * (KMAX + 1) / 2], z[KMAX];
     int S[KMAX];

@@ -119,4 +119,20 @@ BN_HD double score_set_small(const double* __restrict__ C, int64_t ldc, int c, c
   return -((double)n_samples / 2.0) * log(resid2 / syy);
 }
 
+// One shared copy of the K = 8 scorer on the device: the fully unrolled gather + Cholesky is
+// ~2,500 instructions, and the chain kernel reaches it from four places (chain start, the
+// sequential window path, the records of the chain's warp and of its helper warps).  Inlined
+// four times it made up 40 % of a 300 KB kernel that misses the instruction cache on every
+// rarely taken path; as a call it is one copy.  All arguments travel in registers.
+struct Parents8 { int s[8]; };
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+double score_set8(const double* C, int64_t ldc, int c, Parents8 S, int k, int n_samples) {
+  int npd = 0;
+  return score_set_small<8>(C, ldc, c, S.s, k, n_samples, &npd);  // -inf <=> not positive definite
+}
+
 }  // namespace bn
