@@ -41,6 +41,10 @@ constexpr int REC_ACC = 1 << 12;        // checker() accepts (given the iteratio
 constexpr int REC_NPD = 1 << 13;        // non-positive-definite parent Gram
 constexpr int REC_FULLMANY = 1 << 14;   // more than two children were skipped for being at MaxPar
 constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set
+// t_walk: bits 0-7 / 8-15 uniforms consumed when the incoming `valid` flag is 0 / 1 (with the
+// acceptance draw), bits 16 / 17 outgoing `valid`, bits 18 / 19 "this iteration is accepted",
+// bits 20 and 21 record overflow (so that w >> (16 + v) has valid, accept, overflow at bits 0, 2, 4)
+constexpr int WALK_OVF = 3 << 20;
 
 struct ChainParams {  // read-only, shared by all chains of a run
   int P, max_par, W, Ws, n_samples;  // W = words per bitset, Ws = row stride of anc (odd when in smem)
@@ -107,6 +111,8 @@ struct WindowSlots {  // shared memory on the device
   int t_rec[REPLAY_POS];   // REC_* bits
   double t_score[REPLAY_POS];  // score of the proposed parent set
   uint32_t t_full[REPLAY_POS]; // the (up to two) children the draw skipped for being at MaxPar, +1, 16 bits each
+  double t_lu[REPLAY_POS];     // log of the acceptance uniform (accept test in log space)
+  int t_walk[REPLAY_POS];      // what the walk needs of the record, per incoming `valid` v (WALK_* bits)
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
@@ -899,8 +905,8 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
     }
   }
 #undef BN_UAT
-  // the acceptance uniform must be in the ring as well, and the count must fit the record
-  if (i >= hi || i - q > REC_LEN_MASK) ovf = 1;
+  // the acceptance uniform must be in the ring as well, and the count (+1) must fit the record
+  if (i >= hi || i - q >= REC_LEN_MASK) ovf = 1;
   const int ag = (!ovf && p.sim_edge[(int64_t)j + (int64_t)c * P]) ? 1 : 0;
   ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e; ws.t_full[slot] = full;
   ws.t_rec[slot] = (int)(i - q) | (type == 2 ? REC_TYPE : 0) | (cyc ? REC_CYC : 0) | (ovf ? REC_OVF : 0) |
@@ -911,7 +917,7 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
 BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
                          WindowSlots& ws, int slot) {
   int rec = ws.t_rec[slot];
-  if (rec & REC_OVF) return;
+  if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
   const int c = ws.t_c[slot];
   const int type = (rec & REC_TYPE) ? 2 : 1;
   const int ag = (rec & REC_AG) ? 1 : 0;
@@ -922,11 +928,31 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   const double new_prior = prior_value(p.phi, p.omega, (te_new - ag_new) + (p.n_sim_edges - ag_new), te_new);
   // HR = exp(NewLogLike - OldLogLike + NewLogPrior - OldLogPrior), src/network.h:334
   const double arg = sub_rn(add_rn(sub_rn(ws.t_score[slot], m.base[c]), new_prior), old_prior);
-  const double HR = exp(arg);
-  const double u_acc = ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)];
+  // reject iff runif > HR (NaN accepts), :335.  u > exp(arg) <=> log u > arg unless the two are
+  // within rounding of each other: then (and for NaN) the reference's own expression decides.
+  const double d = ws.t_lu[slot] - arg;
+  int accept;
+  if (fabs(d) > 1e-6) {
+    accept = !(d > 0.0);
+  } else {
+    const double HR = exp(arg);
+    const double u_acc = ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)];
+    accept = !(u_acc > HR);
+  }
   rec &= ~REC_ACC;
-  if (!(u_acc > HR)) rec |= REC_ACC;  // reject iff runif > HR (NaN accepts), :335
+  if (accept) rec |= REC_ACC;
   ws.t_rec[slot] = rec;
+  // walk word: an addition sets `valid` itself (src/bayesnet_mcmc.cpp:50), a deletion inherits it
+  const int cons = rec & REC_LEN_MASK;
+  int w;
+  if (type == 1) {
+    const int valid = (rec & REC_CYC) ? 0 : 1;
+    const int len = cons + valid, stop = valid & accept;
+    w = len | (len << 8) | (valid << 16) | (valid << 17) | (stop << 18) | (stop << 19);
+  } else {
+    w = cons | ((cons + 1) << 8) | (1 << 17) | (accept << 19);
+  }
+  ws.t_walk[slot] = w;
 }
 
 BN_HD double nan_sentinel() {
@@ -942,7 +968,8 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
                         WindowSlots& ws, int slot) {
   replay_position(p, m, rc.n_haspar, ubuf, rc.hi, rc.pos + slot, ws, slot);
   const int rec = ws.t_rec[slot];
-  if (rec & REC_OVF) return;
+  if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
+  ws.t_lu[slot] = log(ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)]);
   int kk = 0, npd = 0;
   double sc;
   // the score of a deletion is a function of (child, slot) until the child's parents change:
@@ -1281,18 +1308,22 @@ BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const 
   const int l = Warp::lane();
   int k = *k_io, v = s.valid, n = 0, myk = 0, myvalid = 0, acc = 0, k_acc = 0;
   *ovf = 0;
+  // pointer chase over the walk words: `valid` is only assigned by additions
+  // (src/bayesnet_mcmc.cpp:50-52), the acceptance uniform is drawn for valid iterations only
+  int f = 0;
   while (n < want && k < span_limit) {
-    const int rec = ws.t_rec[k];
-    if (rec & REC_OVF) { *ovf = 1; break; }
-    // `valid` is only assigned by additions (src/bayesnet_mcmc.cpp:50-52)
-    const int valid = (rec & REC_TYPE) ? v : !(rec & REC_CYC);
-    if (l == n) { myk = k; myvalid = valid; }
-    v = valid;
+    const int w = ws.t_walk[k];
+    f = w >> (16 + v);       // bit 0 outgoing valid, bit 2 accepted, bit 4 overflowed record
+    if (f & 0x10) break;
+    if (l == n) { myk = k; myvalid = f & 1; }
     k_acc = k;
-    k += (rec & REC_LEN_MASK) + valid;  // the acceptance uniform is drawn for valid iterations only
+    k += (w >> (v << 3)) & 0xff;
+    v = f & 1;
     n++;
-    if (valid && (rec & REC_ACC)) { acc = 1; break; }
+    if (f & 4) break;
   }
+  if (f & 0x10) *ovf = 1;
+  else if (n > 0 && (f & 4)) acc = 1;
   *accepted = acc;
   if (n == 0) return 0;
   const long long tc = cycle_now();
