@@ -40,11 +40,15 @@ constexpr int REC_AG = 1 << 11;         // edge is in the prior graph
 constexpr int REC_ACC = 1 << 12;        // checker() accepts (given the iteration is valid)
 constexpr int REC_NPD = 1 << 13;        // non-positive-definite parent Gram
 constexpr int REC_FULLMANY = 1 << 14;   // more than two children were skipped for being at MaxPar
+constexpr int REC_STALE = 1 << 15;      // an accepted move of this round changed what the record depends on
 constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set
 // t_walk: bits 0-7 / 8-15 uniforms consumed when the incoming `valid` flag is 0 / 1 (with the
 // acceptance draw), bits 16 / 17 outgoing `valid`, bits 18 / 19 "this iteration is accepted",
 // bits 20 and 21 record overflow (so that w >> (16 + v) has valid, accept, overflow at bits 0, 2, 4)
-constexpr int WALK_OVF = 3 << 20;
+constexpr int WALK_STOP = 3 << 20;            // the walk cannot consume this record, because ...
+constexpr int WALK_OVF = WALK_STOP | (1 << 24);    // ... it ran out of the uniform ring
+constexpr int WALK_STALE = WALK_STOP | (1 << 25);  // ... an accepted move changed what it depends on
+constexpr int WALK_END = WALK_STOP | (1 << 26);    // ... it lies behind the positions of this round
 
 struct ChainParams {  // read-only, shared by all chains of a run
   int P, max_par, W, Ws, n_samples;  // W = words per bitset, Ws = row stride of anc (odd when in smem)
@@ -112,7 +116,8 @@ struct WindowSlots {  // shared memory on the device
   double t_score[REPLAY_POS];  // score of the proposed parent set
   uint32_t t_full[REPLAY_POS]; // the (up to two) children the draw skipped for being at MaxPar, +1, 16 bits each
   double t_lu[REPLAY_POS];     // log of the acceptance uniform (accept test in log space)
-  int t_walk[REPLAY_POS];      // what the walk needs of the record, per incoming `valid` v (WALK_* bits)
+  int t_walk[2 * REPLAY_POS];  // what the walk needs of the record, per incoming `valid` v (WALK_* bits);
+                               // entries REPLAY_POS.. are WALK_END (a step is at most 255 positions)
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
@@ -990,27 +995,30 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
   decide_record(p, m, rc, ubuf, ws, slot);
 }
 
-// after an accepted move at child c: stale records bound the walk, cycle bits and accept
-// decisions are refreshed
-// returns the slot when its record is stale, REPLAY_POS otherwise
+// after an accepted move at child c: records that depend on c's parent list go stale (the
+// walk stops if it lands on one), cycle bits and accept decisions of the others are refreshed
 // `unfull`: the move took c from MaxPar to MaxPar - 1 parents, so draws that skipped c differ
-BN_HD int repair_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
-                        WindowSlots& ws, int slot, int c, int unfull, int from) {
-  if (slot < from) return REPLAY_POS;
+BN_HD void repair_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                         WindowSlots& ws, int slot, int c, int unfull, int from) {
+  if (slot < from) return;
   int rec = ws.t_rec[slot];
-  if (rec & REC_OVF) return REPLAY_POS;
-  if (ws.t_c[slot] == c) return slot;
+  if (rec & (REC_OVF | REC_STALE)) return;
+  bool stale = ws.t_c[slot] == c;
+  if (!stale && unfull && !(rec & REC_TYPE)) {
+    const uint32_t f = ws.t_full[slot], cc = (uint32_t)(c + 1);
+    stale = (rec & REC_FULLMANY) || (f & 0xffffu) == cc || (f >> 16) == cc;
+  }
+  if (stale) {
+    ws.t_rec[slot] = rec | REC_STALE;
+    ws.t_walk[slot] = WALK_STALE;
+    return;
+  }
   if (!(rec & REC_TYPE)) {
-    if (unfull) {
-      const uint32_t f = ws.t_full[slot], cc = (uint32_t)(c + 1);
-      if ((rec & REC_FULLMANY) || (f & 0xffffu) == cc || (f >> 16) == cc) return slot;
-    }
     const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, ws.t_c[slot]) ? 1 : 0;
     rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
     ws.t_rec[slot] = rec;
   }
   decide_record(p, m, rc, ubuf, ws, slot);
-  return REPLAY_POS;
 }
 
 #if defined(__CUDACC__)
@@ -1082,8 +1090,7 @@ __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem
     if (op == HELPER_RECORDS) {
       build_record<KMAX>(p, m, helper_ctx(m), ubuf, ws, slot);
     } else if (op == HELPER_REPAIR) {
-      const int stale = repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[11], m.helper[8]);
-      if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
+      repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[11], m.helper[8]);
     } else if (op == HELPER_ANC_ADD) {
       anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * rows_per_part(p.P, HELPER_WARPS + 1, Warp::NL), part,
                    HELPER_WARPS + 1);
@@ -1114,28 +1121,20 @@ BN_HD void team_records(const ChainParams& p, const ChainMem& m, const RoundCtx&
 #endif
 }
 
-// returns the new span limit
-BN_HD int team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
-                      WindowSlots& ws, int c, int unfull, int from, int span_limit) {
+BN_HD void team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
+                       WindowSlots& ws, int c, int unfull, int from) {
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
-    if (Warp::lane() == 0) { m.helper[8] = from; m.helper[9] = c; m.helper[10] = span_limit; m.helper[11] = unfull; }
+    if (Warp::lane() == 0) { m.helper[8] = from; m.helper[9] = c; m.helper[11] = unfull; }
     helper_post(m, HELPER_REPAIR, rc);
     cta_bar(1);
-    const int stale = repair_record(p, m, rc, ubuf, ws, Warp::lane(), c, unfull, from);
-    if (stale < REPLAY_POS) atomicMin((int*)&m.helper[10], stale);
+    repair_record(p, m, rc, ubuf, ws, Warp::lane(), c, unfull, from);
     cta_bar(2);
-    return m.helper[10];
   }
-  return 0;
 #else
-  int lim = span_limit;
-  for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL) {
-    const int stale = repair_record(p, m, rc, ubuf, ws, slot, c, unfull, from);
-    lim = stale < lim ? stale : lim;
-  }
+  for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL)
+    repair_record(p, m, rc, ubuf, ws, slot, c, unfull, from);
   Warp::sync();
-  return Warp::min(lim);
 #endif
 }
 
@@ -1302,28 +1301,30 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
 // iterations, stopping behind the first accepted one) and commit them -- the same bookkeeping
 // as commit(), with the slot of iteration s.iter + q living in the registers of lane q.
 // Returns the number of iterations committed; *accepted / *acc_c / *acc_type describe the
-// accepted move, *ovf an overflowed record in front of the walk.
+// accepted move, *stop (WALK_OVF / WALK_STALE / WALK_END or 0) the record that ended the walk.
 BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const WindowSlots& ws, int64_t round_pos,
-                      int* k_io, int span_limit, int want, int* ovf, int* accepted, int* acc_c, int* acc_type) {
+                      int* k_io, int want, int* stop, int* accepted, int* acc_c, int* acc_type) {
   const int l = Warp::lane();
   int k = *k_io, v = s.valid, n = 0, myk = 0, myvalid = 0, acc = 0, k_acc = 0;
-  *ovf = 0;
+  *stop = 0;
   // pointer chase over the walk words: `valid` is only assigned by additions
   // (src/bayesnet_mcmc.cpp:50-52), the acceptance uniform is drawn for valid iterations only
-  int f = 0;
-  while (n < want && k < span_limit) {
+  // (records that cannot be consumed -- overflow, stale, behind the round -- carry a stop mark,
+  // so the loop has one rarely taken exit besides its counter)
+  while (n < want) {
     const int w = ws.t_walk[k];
-    f = w >> (16 + v);       // bit 0 outgoing valid, bit 2 accepted, bit 4 overflowed record
-    if (f & 0x10) break;
+    const int f = w >> (16 + v);  // bit 0 outgoing valid, bit 2 accepted, bit 4 stop mark
+    if (f & 0x14) {
+      if (f & 0x10) { *stop = w; break; }
+      acc = 1;
+    }
     if (l == n) { myk = k; myvalid = f & 1; }
     k_acc = k;
     k += (w >> (v << 3)) & 0xff;
     v = f & 1;
     n++;
-    if (f & 4) break;
+    if (acc) break;
   }
-  if (f & 0x10) *ovf = 1;
-  else if (n > 0 && (f & 4)) acc = 1;
   *accepted = acc;
   if (n == 0) return 0;
   const long long tc = cycle_now();
@@ -1404,35 +1405,35 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   team_records<KMAX>(p, m, rc, rng.ubuf, ws);
   long long t1 = cycle_now();
   s.cyc[1] += t1 - t0;
-  int k = 0, span_limit = REPLAY_POS;
+  int k = 0;
   for (;;) {
     t0 = cycle_now();
     int want = WIN < Warp::NL ? WIN : Warp::NL;  // one lane per iteration of the epoch
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     if (want <= 0) break;
-    int ovf = 0, accepted = 0, c = 0, type = 0;
+    int stop = 0, accepted = 0, c = 0, type = 0;
     const int k0 = k, nh0 = s.n_haspar;
-    const int n = round_epoch(p, m, s, ws, rc.pos, &k, span_limit, want, &ovf, &accepted, &c, &type);
+    const int n = round_epoch(p, m, s, ws, rc.pos, &k, want, &stop, &accepted, &c, &type);
     s.cyc[2] += cycle_now() - t0;
     if (n == 0) {
       // one iteration needs more uniforms than a record can count: the sequential path takes it
-      if (ovf && k0 == 0) s.need_full = 1;
+      if (stop == WALK_OVF && k0 == 0) s.need_full = 1;
       break;
     }
     s.need_full = 0;
     s.slots_sim += n;
-    if (ovf || k >= span_limit) break;
+    if (stop) break;  // the next record is overflowed, stale or behind this round's positions
     if (accepted) {
       // moves that invalidate every record: the set of nodes with parents changed (deletion
       // draws index into it), TotalEdges < 4.  A child that reaches MaxPar only affects its own
       // records; one that drops below it affects the draws that skipped it.
       if (s.n_haspar != nh0 || s.te_true < 4) break;
+      if (k >= REPLAY_POS) break;
       const int unfull = (type == 2 && m.npar[c] == p.max_par - 1) ? 1 : 0;
       t0 = cycle_now();
       rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
-      span_limit = team_repair(p, m, rc, rng.ubuf, ws, c, unfull, k, span_limit);
+      team_repair(p, m, rc, rng.ubuf, ws, c, unfull, k);
       s.cyc[2] += cycle_now() - t0;
-      if (k >= span_limit) break;
     }
   }
 }
@@ -1445,6 +1446,8 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
                      WindowSlots& ws) {
   const int l = Warp::lane();
   chain_init<KMAX>(p, m, s);
+  for (int i = REPLAY_POS + l; i < 2 * REPLAY_POS; i += Warp::NL) ws.t_walk[i] = WALK_END;
+  Warp::sync();
 #if defined(__CUDA_ARCH__)
   const WhJump jump = wh_jump_for_thread();
 #endif
