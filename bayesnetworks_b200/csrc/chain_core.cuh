@@ -41,7 +41,8 @@ constexpr int REC_ACC = 1 << 12;        // checker() accepts (given the iteratio
 constexpr int REC_NPD = 1 << 13;        // non-positive-definite parent Gram
 constexpr int REC_FULLMANY = 1 << 14;   // more than two children were skipped for being at MaxPar
 constexpr int REC_STALE = 1 << 15;      // an accepted move of this round changed what the record depends on
-constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set
+constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set (7 bits)
+constexpr int REC_NOSCORE = 1 << 23;    // cyclic when built: never scored (stale if the cycle bit clears)
 // t_walk: bits 0-7 / 8-15 uniforms consumed when the incoming `valid` flag is 0 / 1 (with the
 // acceptance draw), bits 16 / 17 outgoing `valid`, bits 18 / 19 "this iteration is accepted",
 // bits 20 and 21 record overflow (so that w >> (16 + v) has valid, accept, overflow at bits 0, 2, 4)
@@ -925,6 +926,12 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
   const int c = ws.t_c[slot];
   const int type = (rec & REC_TYPE) ? 2 : 1;
+  if (type == 1 && (rec & REC_CYC)) {
+    // invalid addition: no checker(), no acceptance draw
+    const int len = rec & REC_LEN_MASK;
+    ws.t_walk[slot] = len | (len << 8);
+    return;
+  }
   const int ag = (rec & REC_AG) ? 1 : 0;
   const int te_new = rc.te_true + (type == 1 ? 1 : -1);
   const int ag_new = rc.agree_true + (type == 1 ? ag : -ag);
@@ -951,9 +958,8 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   const int cons = rec & REC_LEN_MASK;
   int w;
   if (type == 1) {
-    const int valid = (rec & REC_CYC) ? 0 : 1;
-    const int len = cons + valid, stop = valid & accept;
-    w = len | (len << 8) | (valid << 16) | (valid << 17) | (stop << 18) | (stop << 19);
+    const int len = cons + 1;
+    w = len | (len << 8) | (3 << 16) | (accept << 18) | (accept << 19);
   } else {
     w = cons | ((cons + 1) << 8) | (1 << 17) | (accept << 19);
   }
@@ -974,6 +980,13 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
   replay_position(p, m, rc.n_haspar, ubuf, rc.hi, rc.pos + slot, ws, slot);
   const int rec = ws.t_rec[slot];
   if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
+  if (!(rec & REC_TYPE) && (rec & REC_CYC)) {
+    // a cyclic addition never reaches checker(): it is not scored; should an accepted deletion
+    // clear its cycle bit later in the round, the record goes stale instead
+    ws.t_rec[slot] = rec | REC_NOSCORE;
+    decide_record(p, m, rc, ubuf, ws, slot);
+    return;
+  }
   ws.t_lu[slot] = log(ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)]);
   int kk = 0, npd = 0;
   double sc;
@@ -1015,6 +1028,11 @@ BN_HD void repair_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   }
   if (!(rec & REC_TYPE)) {
     const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, ws.t_c[slot]) ? 1 : 0;
+    if (!cyc && (rec & REC_NOSCORE)) {
+      ws.t_rec[slot] = rec | REC_STALE;
+      ws.t_walk[slot] = WALK_STALE;
+      return;
+    }
     rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
     ws.t_rec[slot] = rec;
   }
