@@ -184,6 +184,9 @@ BN_HD void hp_remove(ChainMem& m, int n_before, int c) {
 // ---------------------------------------------------------------------------
 struct alignas(16) U4 { uint32_t x, y, z, w; };
 BN_HD U4 or4(U4 a, U4 b) { U4 r; r.x = a.x | b.x; r.y = a.y | b.y; r.z = a.z | b.z; r.w = a.w | b.w; return r; }
+BN_HD U4 andn4(U4 a, U4 b) { U4 r; r.x = a.x & ~b.x; r.y = a.y & ~b.y; r.z = a.z & ~b.z; r.w = a.w & ~b.w; return r; }
+BN_HD U4 and4(U4 a, U4 b) { U4 r; r.x = a.x & b.x; r.y = a.y & b.y; r.z = a.z & b.z; r.w = a.w & b.w; return r; }
+BN_HD bool nz4(U4 a) { return (a.x | a.y | a.z | a.w) != 0u; }
 BN_HD bool ne4(U4 a, U4 b) { return ((a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w)) != 0u; }
 BN_HD int popc4(U4 a) { return popc32(a.x) + popc32(a.y) + popc32(a.z) + popc32(a.w); }
 BN_HD U4 with_bit(U4 v, int b) {  // set bit b (0..127) of the chunk
@@ -279,7 +282,26 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
   const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr;
   const int n = collect_desc_part(p, m, c, 1, list, part, nparts);
   const U4* aj = (const U4*)(m.anc + (uint32_t)j * (uint32_t)p.Ws);
-  if (g.chunks <= g.lpr) {
+  if (g.chunks == 8 && Warp::NL == 32) {
+    // 897..1,024 nodes: 8 lanes per row, 4 rows per pass, four passes in flight.  A pass index
+    // behind the list repeats the lane group's first row (the OR is idempotent), so the loop
+    // body carries no predicates.
+    const int sub8 = l >> 3, li8 = l & 7;
+    const U4 a = aj[li8];  // row j holds j itself
+    for (int r0 = sub8; r0 < n; r0 += 16) {
+      U4* ad[4];
+      U4 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int r = (r0 + 4 * t < n) ? r0 + 4 * t : r0;
+        ad[t] = (U4*)(m.anc + (uint32_t)list[r] * (uint32_t)p.Ws) + li8;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; t++) v[t] = *ad[t];
+#pragma unroll
+      for (int t = 0; t < 4; t++) *ad[t] = or4(v[t], a);
+    }
+  } else if (g.chunks <= g.lpr) {
     // one 128-bit chunk per lane (up to 4,096 nodes): the source chunk stays in registers
     U4 a = {0u, 0u, 0u, 0u};
     if (li < g.chunks) {
@@ -336,6 +358,17 @@ BN_HD void team_sync(const ChainMem& m) {
 }
 
 BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
+  {
+    // j (and with it all its ancestors) already an ancestor of c: row j is contained in row c and
+    // in the row of every descendant of c -- nothing changes (a redundant edge, common in a
+    // dense graph)
+    const RowGeom g = row_geom(p);
+    const U4* aj = (const U4*)(m.anc + (uint32_t)j * (uint32_t)p.Ws);
+    const U4* ac = (const U4*)(m.anc + (uint32_t)c * (uint32_t)p.Ws);
+    int news = 0;
+    for (int ch = Warp::lane(); ch < g.chunks; ch += Warp::NL) news |= nz4(andn4(aj[ch], ac[ch])) ? 1 : 0;
+    if (Warp::ballot(news) == 0u) return;
+  }
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
     if (Warp::lane() == 0) { m.helper[8] = j; m.helper[9] = c; m.helper[0] = HELPER_ANC_ADD; }
@@ -392,9 +425,6 @@ BN_HD DelLayout del_layout(const ChainParams& p, const ChainMem& m, int nparts) 
   d.nzc = (int*)(d.dirty + 3 * p.W + 4);  // [0] = number of chunks where L != 0, then their indices
   return d;
 }
-BN_HD U4 andn4(U4 a, U4 b) { U4 r; r.x = a.x & ~b.x; r.y = a.y & ~b.y; r.z = a.z & ~b.z; r.w = a.w & ~b.w; return r; }
-BN_HD U4 and4(U4 a, U4 b) { U4 r; r.x = a.x & b.x; r.y = a.y & b.y; r.z = a.z & b.z; r.w = a.w & b.w; return r; }
-BN_HD bool nz4(U4 a) { return (a.x | a.y | a.z | a.w) != 0u; }
 
 BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts) {
   const int l = Warp::lane(), W = p.W, MP = p.max_par;
