@@ -210,9 +210,10 @@ class Context:
         kind = _RNG_KINDS[rng]
         p, mp = self.n_nodes, self.max_par
         cap = max(1, (n_iter + output - 1) // output)
-        ints = {k: np.zeros((n_chains, cap), dtype=np.int32) for k in
+        # (np.empty: bn_run overwrites every row up to n_rows, and only those are handed out)
+        ints = {k: np.empty((n_chains, cap), dtype=np.int32) for k in
                 ("iter", "ChangedNode", "movetype", "additions", "deletions", "FN", "FP")}
-        gll = np.zeros((n_chains, cap))
+        gll = np.empty((n_chains, cap))
         n_rows = np.zeros(n_chains, dtype=np.int32)
         tr = _lib.Trace(cap, n_rows.ctypes.data_as(_lib._ip), ints["iter"].ctypes.data_as(_lib._ip),
                         ints["ChangedNode"].ctypes.data_as(_lib._ip),
@@ -257,16 +258,14 @@ class Context:
             args.edge_freq = freq.ctypes.data_as(_lib._ip)
             nfreq = np.zeros((n_chains, p, mp + 1), dtype=np.int32)
             args.npar_freq = nfreq.ctypes.data_as(_lib._ip)
-        fpar = np.full((n_chains, p, mp), -1, dtype=np.int32)
-        fnpar = np.zeros((n_chains, p), dtype=np.int32)
+        fpar = np.empty((n_chains, p, mp), dtype=np.int32)   # the library pads unused slots with -1
+        fnpar = np.empty((n_chains, p), dtype=np.int32)
         stats = (_lib.ChainStats * n_chains)()
         ms = C.c_float(0)
         status = L.bn_run(self._h, C.byref(args), C.byref(tr), ptr(fpar), ptr(fnpar),
                           C.cast(stats, C.c_void_p), C.byref(ms))
         check(status)
-        # unused parent slots read -1; everything below is views / one vectorised pass (the
-        # per-chain Python work is part of every end-to-end step)
-        fpar = np.where(np.arange(mp, dtype=np.int32)[None, None, :] < fnpar[:, :, None], fpar, np.int32(-1))
+        # everything below is views (the per-chain Python work is part of every end-to-end step)
         st = np.frombuffer(stats, dtype=_lib.CHAIN_STATS_DTYPE, count=n_chains)
         out = []
         for ch in range(n_chains):

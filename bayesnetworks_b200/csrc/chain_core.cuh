@@ -1229,7 +1229,8 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
   }
   if (type == 1) {
     if (l == 0) {
-      pc[k] = j; bc[k] = (int)first_counted; m.npar[c] = k + 1;
+      pc[k] = j; m.npar[c] = k + 1;
+      if (m.edge_freq) bc[k] = (int)first_counted;  // birth iterations only feed the tabulation
       m.base[c] = new_score;
     }
     if (k == 0) {
@@ -1247,7 +1248,9 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
         const int64_t cnt = first_counted - bc[del];
         if (cnt > 0) m.edge_freq[(int64_t)j + (int64_t)c * p.P] += (int)cnt;
       }
-      for (int e = del; e + 1 < k; e++) { pc[e] = pc[e + 1]; bc[e] = bc[e + 1]; }
+      for (int e = del; e + 1 < k; e++) pc[e] = pc[e + 1];
+      if (m.edge_freq)
+        for (int e = del; e + 1 < k; e++) bc[e] = bc[e + 1];
       pc[k - 1] = -1;
       m.npar[c] = k - 1;
       m.base[c] = new_score;
