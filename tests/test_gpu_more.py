@@ -41,6 +41,23 @@ def test_dense_synthetic_vs_oracle(oracle, max_par, omega):
     assert ref.deletions[-1] > 100
 
 
+@pytest.mark.parametrize("seed,P,max_par,omega", [(11, 30, 3, 0.3), (12, 48, 4, 0.4), (13, 64, 6, 0.25),
+                                                   (14, 36, 8, 0.6), (15, 90, 5, 0.35)])
+def test_random_dense_graphs_vs_oracle(oracle, seed, P, max_par, omega):
+    """More seeds / shapes in the dense regime (many accepted moves per round: record repair,
+    stale marks, nodes entering and leaving MaxPar, nodes losing their last parent)."""
+    from bayesnetworks_b200 import Context
+    from oracle.oracle import RNG_WH
+    X, g, nt = _synthetic(P, 400, max_par, seed)
+    sd = (100 + seed, 200 + seed, 300 + seed)
+    ref = oracle.mcmc(X, g.source, g.target, nt, max_par=max_par, omega=omega, n_iter=12000, output=11,
+                      rng_kind=RNG_WH, seeds=sd)
+    with Context.from_data(X, g.source, g.target, nt, max_par=max_par, omega=omega) as ctx:
+        r = ctx.run(n_iter=12000, output=11, rng="wh", seeds=sd, log_moves=True)[0][0]
+    _same_trace(r, ref, 400)
+    assert ref.deletions[-1] > 50
+
+
 def test_config3_shape_vs_oracle(oracle):
     """BASELINE config 3 shape (100 nodes x 10,000 samples), shortened to what the oracle's
     O(N) residual pass finishes in seconds."""
