@@ -43,6 +43,8 @@ constexpr int REC_FULLMANY = 1 << 14;   // more than two children were skipped f
 constexpr int REC_STALE = 1 << 15;      // an accepted move of this round changed what the record depends on
 constexpr int REC_KK_SHIFT = 16;        // size of the scored parent set (7 bits)
 constexpr int REC_NOSCORE = 1 << 23;    // cyclic when built: never scored (stale if the cycle bit clears)
+constexpr int REC_CLOSE = 1 << 24;      // log u within 1e-6 of the log Hastings ratio: decided by the
+                                        // reference's own expression, stale after any accepted move
 // t_walk: bits 0-7 / 8-15 uniforms consumed when the incoming `valid` flag is 0 / 1 (with the
 // acceptance draw), bits 16 / 17 outgoing `valid`, bits 18 / 19 "this iteration is accepted",
 // bits 20 and 21 record overflow (so that w >> (16 + v) has valid, accept, overflow at bits 0, 2, 4)
@@ -102,6 +104,7 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int win;             // current window size
   int windows;
   int need_full;       // the last round could not start: top the ring up completely before retrying
+  int anc_changed;     // the last accepted move changed ancestor rows (else no cycle bit can differ)
   int status;
 };
 
@@ -357,7 +360,7 @@ BN_HD void team_sync(const ChainMem& m) {
   Warp::sync();
 }
 
-BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
+BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c, int& m_anc_changed) {
   {
     // j (and with it all its ancestors) already an ancestor of c: row j is contained in row c and
     // in the row of every descendant of c -- nothing changes (a redundant edge, common in a
@@ -367,8 +370,9 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c) {
     const U4* ac = (const U4*)(m.anc + (uint32_t)c * (uint32_t)p.Ws);
     int news = 0;
     for (int ch = Warp::lane(); ch < g.chunks; ch += Warp::NL) news |= nz4(andn4(aj[ch], ac[ch])) ? 1 : 0;
-    if (Warp::ballot(news) == 0u) return;
+    if (Warp::ballot(news) == 0u) { m_anc_changed = 0; return; }
   }
+  m_anc_changed = 1;
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
     if (Warp::lane() == 0) { m.helper[8] = j; m.helper[9] = c; m.helper[0] = HELPER_ANC_ADD; }
@@ -534,7 +538,7 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
   }
 }
 
-BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
+BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc_changed) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane();
   int nparts = 1;
@@ -559,8 +563,9 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c) {
       lay.L[ch] = lost;
       if (nz4(lost)) { ac[ch] = v; changed = 1; }
     }
-    if (Warp::ballot(changed) == 0u) return;
+    if (Warp::ballot(changed) == 0u) { m_anc_changed = 0; return; }
   }
+  m_anc_changed = 1;
   for (int w = l; w < 3 * p.W + 4; w += Warp::NL) lay.dirty[w] = 0u;  // three bitsets + four flags
   Warp::sync();
   {
@@ -949,17 +954,25 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
                    (ag ? REC_AG : 0) | (many ? REC_FULLMANY : 0);
 }
 
-// checker() for a record under the current global counts: sets REC_AG / REC_ACC
+// what the walk needs of a (consumable) record: an addition sets `valid` itself
+// (src/bayesnet_mcmc.cpp:50), a deletion inherits it; invalid iterations draw no acceptance uniform
+BN_HD int walk_word(int rec) {
+  const int cons = rec & REC_LEN_MASK, accept = (rec & REC_ACC) ? 1 : 0;
+  if (rec & REC_TYPE) return cons | ((cons + 1) << 8) | (1 << 17) | (accept << 19);
+  if (rec & REC_CYC) return cons | (cons << 8);
+  const int len = cons + 1;
+  return len | (len << 8) | (3 << 16) | (accept << 18) | (accept << 19);
+}
+
+// checker() for a record under the current global counts: sets REC_ACC / REC_CLOSE and the walk word
 BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
                          WindowSlots& ws, int slot) {
   int rec = ws.t_rec[slot];
   if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
   const int c = ws.t_c[slot];
   const int type = (rec & REC_TYPE) ? 2 : 1;
-  if (type == 1 && (rec & REC_CYC)) {
-    // invalid addition: no checker(), no acceptance draw
-    const int len = rec & REC_LEN_MASK;
-    ws.t_walk[slot] = len | (len << 8);
+  if (type == 1 && (rec & REC_CYC)) {  // invalid addition: no checker(), no acceptance draw
+    ws.t_walk[slot] = walk_word(rec);
     return;
   }
   const int ag = (rec & REC_AG) ? 1 : 0;
@@ -972,28 +985,23 @@ BN_HD void decide_record(const ChainParams& p, const ChainMem& m, const RoundCtx
   const double arg = sub_rn(add_rn(sub_rn(ws.t_score[slot], m.base[c]), new_prior), old_prior);
   // reject iff runif > HR (NaN accepts), :335.  u > exp(arg) <=> log u > arg unless the two are
   // within rounding of each other: then (and for NaN) the reference's own expression decides.
+  // A move at ANOTHER node changes arg only by the rounding of the two prior expressions
+  // (NewLogPrior - OldLogPrior is -phi (1 - 2 ag) -/+ omega whatever the counts), so outside the
+  // 1e-6 band the decision stands for the rest of the round; inside it the record is marked.
   const double d = ws.t_lu[slot] - arg;
   int accept;
+  rec &= ~(REC_ACC | REC_CLOSE);
   if (fabs(d) > 1e-6) {
     accept = !(d > 0.0);
   } else {
     const double HR = exp(arg);
     const double u_acc = ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)];
     accept = !(u_acc > HR);
+    rec |= REC_CLOSE;
   }
-  rec &= ~REC_ACC;
   if (accept) rec |= REC_ACC;
   ws.t_rec[slot] = rec;
-  // walk word: an addition sets `valid` itself (src/bayesnet_mcmc.cpp:50), a deletion inherits it
-  const int cons = rec & REC_LEN_MASK;
-  int w;
-  if (type == 1) {
-    const int len = cons + 1;
-    w = len | (len << 8) | (3 << 16) | (accept << 18) | (accept << 19);
-  } else {
-    w = cons | ((cons + 1) << 8) | (1 << 17) | (accept << 19);
-  }
-  ws.t_walk[slot] = w;
+  ws.t_walk[slot] = walk_word(rec);
 }
 
 BN_HD double nan_sentinel() {
@@ -1038,35 +1046,36 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
   decide_record(p, m, rc, ubuf, ws, slot);
 }
 
-// after an accepted move at child c: records that depend on c's parent list go stale (the
-// walk stops if it lands on one), cycle bits and accept decisions of the others are refreshed
+// after an accepted move at child c: records that depend on c's parent list go stale (the walk
+// stops if it lands on one), as do the close calls; the others keep their decision, and when
+// ancestor rows changed (`retest`) the additions get their cycle bit re-tested.
 // `unfull`: the move took c from MaxPar to MaxPar - 1 parents, so draws that skipped c differ
-BN_HD void repair_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
-                         WindowSlots& ws, int slot, int c, int unfull, int from) {
+BN_HD void repair_record(const ChainParams& p, const ChainMem& m, WindowSlots& ws, int slot, int c, int unfull,
+                         int retest, int from) {
   if (slot < from) return;
   int rec = ws.t_rec[slot];
   if (rec & (REC_OVF | REC_STALE)) return;
-  bool stale = ws.t_c[slot] == c;
+  bool stale = ws.t_c[slot] == c || (rec & REC_CLOSE);
   if (!stale && unfull && !(rec & REC_TYPE)) {
     const uint32_t f = ws.t_full[slot], cc = (uint32_t)(c + 1);
     stale = (rec & REC_FULLMANY) || (f & 0xffffu) == cc || (f >> 16) == cc;
   }
+  if (!stale && retest && !(rec & REC_TYPE)) {
+    const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, ws.t_c[slot]) ? 1 : 0;
+    if (cyc != ((rec & REC_CYC) ? 1 : 0)) {
+      if (!cyc && (rec & REC_NOSCORE)) {
+        stale = true;  // it was never scored
+      } else {
+        rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
+        ws.t_rec[slot] = rec;
+        ws.t_walk[slot] = walk_word(rec);
+      }
+    }
+  }
   if (stale) {
     ws.t_rec[slot] = rec | REC_STALE;
     ws.t_walk[slot] = WALK_STALE;
-    return;
   }
-  if (!(rec & REC_TYPE)) {
-    const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, ws.t_c[slot]) ? 1 : 0;
-    if (!cyc && (rec & REC_NOSCORE)) {
-      ws.t_rec[slot] = rec | REC_STALE;
-      ws.t_walk[slot] = WALK_STALE;
-      return;
-    }
-    rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
-    ws.t_rec[slot] = rec;
-  }
-  decide_record(p, m, rc, ubuf, ws, slot);
 }
 
 #if defined(__CUDACC__)
@@ -1138,7 +1147,7 @@ __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem
     if (op == HELPER_RECORDS) {
       build_record<KMAX>(p, m, helper_ctx(m), ubuf, ws, slot);
     } else if (op == HELPER_REPAIR) {
-      repair_record(p, m, helper_ctx(m), ubuf, ws, slot, m.helper[9], m.helper[11], m.helper[8]);
+      repair_record(p, m, ws, slot, m.helper[9], m.helper[11], m.helper[7], m.helper[8]);
     } else if (op == HELPER_ANC_ADD) {
       anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * rows_per_part(p.P, HELPER_WARPS + 1, Warp::NL), part,
                    HELPER_WARPS + 1);
@@ -1169,19 +1178,23 @@ BN_HD void team_records(const ChainParams& p, const ChainMem& m, const RoundCtx&
 #endif
 }
 
-BN_HD void team_repair(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
-                       WindowSlots& ws, int c, int unfull, int from) {
+// `retest` = the move changed ancestor rows: the cycle bits of the additions are re-tested
+BN_HD void team_repair(const ChainParams& p, const ChainMem& m, WindowSlots& ws, int c, int unfull, int retest,
+                       int from) {
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
-    if (Warp::lane() == 0) { m.helper[8] = from; m.helper[9] = c; m.helper[11] = unfull; }
-    helper_post(m, HELPER_REPAIR, rc);
+    if (Warp::lane() == 0) {
+      m.helper[8] = from; m.helper[9] = c; m.helper[11] = unfull; m.helper[7] = retest;
+      m.helper[0] = HELPER_REPAIR;
+    }
+    Warp::sync();
     cta_bar(1);
-    repair_record(p, m, rc, ubuf, ws, Warp::lane(), c, unfull, from);
+    repair_record(p, m, ws, Warp::lane(), c, unfull, retest, from);
     cta_bar(2);
   }
 #else
   for (int slot = Warp::lane(); slot < REPLAY_POS; slot += Warp::NL)
-    repair_record(p, m, rc, ubuf, ws, slot, c, unfull, from);
+    repair_record(p, m, ws, slot, c, unfull, retest, from);
   Warp::sync();
 #endif
 }
@@ -1241,7 +1254,7 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     }
     s.te_true++; s.agree_true += ag;
     Warp::sync();
-    anc_after_add(p, m, j, c);
+    anc_after_add(p, m, j, c, s.anc_changed);
   } else {
     if (l == 0) {
       if (m.edge_freq) {
@@ -1263,7 +1276,7 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     }
     s.te_true--; s.agree_true -= ag;
     Warp::sync();
-    anc_after_delete(p, m, c);
+    anc_after_delete(p, m, c, s.anc_changed);
   }
   if (m.dscore)  // the deletion scores of c are no longer valid
     for (int e = l; e < MP; e += Warp::NL) m.dscore[(int64_t)c * MP + e] = nan_sentinel();
@@ -1482,8 +1495,7 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
       if (k >= REPLAY_POS) break;
       const int unfull = (type == 2 && m.npar[c] == p.max_par - 1) ? 1 : 0;
       t0 = cycle_now();
-      rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
-      team_repair(p, m, rc, rng.ubuf, ws, c, unfull, k);
+      team_repair(p, m, ws, c, unfull, s.anc_changed, k);
       s.cyc[2] += cycle_now() - t0;
     }
   }
