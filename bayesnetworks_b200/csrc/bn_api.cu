@@ -256,7 +256,10 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
 }
 
 // X on the device (dX, ldx) -> d_C.  If inplace, dX is the context's padded buffer.
-static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc, const GramPlan& pl) {
+// hX != NULL: X is still in host memory; its H2D copy into dXc is pipelined with the build
+// (gram_build_from_host), one block of 128 columns at a time on a second stream.
+static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc, const GramPlan& pl,
+                          const double* hX = nullptr) {
   double *d_partial = nullptr, *d_scratch = nullptr;
   int* d_flag = nullptr;
   StageTimer tm("ctx_build_gram");
@@ -267,12 +270,34 @@ static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc,
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (e1 != cudaSuccess || e2 != cudaSuccess) rc = fail(BN_ERR_OOM, "gram scratch allocation failed");
   tm.lap("workspace");
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> arrived;
   if (!rc) {
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);
     cudaEventRecord(ev0, c->stream);
-    const char* msg = gram_build(dX, ldx, c->n_samples, c->P, dXc, pl.ld_centered, d_partial, pl, c->d_colsum,
-                                 c->d_mean, c->d_C, c->P, d_scratch, d_flag, c->stream, &c->launches);
-    if (msg) rc = fail(BN_ERR_CUDA, "gram_build: %s", msg);
+    const char* msg;
+    if (hX) {
+      if (cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        rc = fail(BN_ERR_CUDA, "cannot create the copy stream");
+      } else {
+        arrived.resize(pl.n_tiles);
+        for (auto& e : arrived) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        // the copy stream must not start before whatever the compute stream was asked to do first
+        cudaEvent_t start;
+        cudaEventCreateWithFlags(&start, cudaEventDisableTiming);
+        cudaEventRecord(start, c->stream);
+        cudaStreamWaitEvent(copy_stream, start, 0);
+        cudaEventDestroy(start);
+        msg = gram_build_from_host(hX, c->n_samples, c->P, dXc, pl.ld_centered, d_partial, pl, c->d_colsum,
+                                   c->d_mean, c->d_C, c->P, d_scratch, d_flag, c->stream, copy_stream,
+                                   arrived.data(), &c->launches);
+        if (msg) rc = fail(BN_ERR_CUDA, "gram_build_from_host: %s", msg);
+      }
+    } else {
+      msg = gram_build(dX, ldx, c->n_samples, c->P, dXc, pl.ld_centered, d_partial, pl, c->d_colsum,
+                       c->d_mean, c->d_C, c->P, d_scratch, d_flag, c->stream, &c->launches);
+      if (msg) rc = fail(BN_ERR_CUDA, "gram_build: %s", msg);
+    }
   }
   if (!rc) {
     launch_diag(c->d_C, c->P, c->P, c->d_diag, c->stream);
@@ -290,6 +315,8 @@ static int ctx_build_gram(bn_ctx* c, const double* dX, int64_t ldx, double* dXc,
   }
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+  for (auto& e : arrived) cudaEventDestroy(e);
   pool_free(d_partial); pool_free(d_scratch); pool_free(d_flag);
   tm.lap("launch + sync (incl. pending H2D)");
   return rc;
@@ -308,15 +335,9 @@ extern "C" int bn_create(const double* X, int n_samples, int P, const int* src, 
   cudaError_t e = pool_alloc((void**)&dXc, (size_t)pl.ld_centered * P * sizeof(double));
   if (e != cudaSuccess) { bn_destroy(c); *out = nullptr; return fail(BN_ERR_OOM, "cannot allocate the device copy of X"); }
   tm.lap("alloc device copy of X");
-  // column p of the R matrix is contiguous: one pitched copy into the padded buffer
-  if (pl.ld_centered == n_samples)
-    e = cudaMemcpyAsync(dXc, X, (size_t)n_samples * P * 8, cudaMemcpyHostToDevice, c->stream);
-  else
-    e = cudaMemcpy2DAsync(dXc, (size_t)pl.ld_centered * 8, X, (size_t)n_samples * 8, (size_t)n_samples * 8,
-                          (size_t)P, cudaMemcpyHostToDevice, c->stream);
-  if (e != cudaSuccess) rc = fail(BN_ERR_CUDA, "H2D copy of X: %s", cudaGetErrorString(e));
-  tm.lap("enqueue H2D");
-  if (!rc) rc = ctx_build_gram(c, dXc, pl.ld_centered, dXc, pl);  // centred in place
+  // column p of the R matrix is contiguous: the copy into the padded buffer goes block of
+  // columns by block of columns, overlapped with the build (centred in place)
+  if (!rc) rc = ctx_build_gram(c, dXc, pl.ld_centered, dXc, pl, X);
   pool_free(dXc);
   if (rc) { bn_destroy(c); *out = nullptr; }
   return rc;

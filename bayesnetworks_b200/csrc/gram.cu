@@ -142,20 +142,31 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 // the row panels).
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_dmma_kernel(const __grid_constant__ CUtensorMap tmap, int n_tiles, int n_pairs,
-                 int stages_total, int n_splits, double* __restrict__ partial, int* __restrict__ error_flag) {
+                 int stages_total, int n_splits, double* __restrict__ partial, int* __restrict__ error_flag,
+                 int tj_only) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + NSTAGE * STAGE_BYTES);
   uint64_t* empty = full + NSTAGE;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x;
-  const int split = item / n_pairs;
-  int pair = item - split * n_pairs;
-  // unrank the upper-triangular pair index: rows ti have (n_tiles - ti) entries
-  int ti = 0;
-  while (pair >= n_tiles - ti) { pair -= n_tiles - ti; ti++; }
-  const int tj = ti + pair;
+  // tj_only < 0: the grid covers every (split, pair).  tj_only >= 0: only the pairs whose
+  // second tile is tj_only (those that become computable when that block of columns has
+  // arrived from the host); the partial tile lands in the same slot either way.
+  int split, ti, tj;
+  if (tj_only < 0) {
+    split = blockIdx.x / n_pairs;
+    int pair = blockIdx.x - split * n_pairs;
+    // unrank the upper-triangular pair index: rows ti have (n_tiles - ti) entries
+    ti = 0;
+    while (pair >= n_tiles - ti) { pair -= n_tiles - ti; ti++; }
+    tj = ti + pair;
+  } else {
+    split = blockIdx.x / (tj_only + 1);
+    ti = blockIdx.x - split * (tj_only + 1);
+    tj = tj_only;
+  }
+  const int item = split * n_pairs + ti * n_tiles - (ti * (ti - 1)) / 2 + (tj - ti);
   const bool diag = (ti == tj);
 
   const int per = (stages_total + n_splits - 1) / n_splits;
@@ -360,12 +371,72 @@ const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, doub
     return "cudaFuncSetAttribute(gram_dmma_kernel) failed";
   cudaMemsetAsync(d_error_flag, 0, sizeof(int), stream);
   gram_dmma_kernel<<<(unsigned)pl.items, GRAM_THREADS, GRAM_SMEM, stream>>>(
-      tmap, pl.n_tiles, pl.n_pairs, pl.stages_total, pl.n_splits, d_partial, d_error_flag);
+      tmap, pl.n_tiles, pl.n_pairs, pl.stages_total, pl.n_splits, d_partial, d_error_flag, -1);
   // 4. reduce
   const int64_t total = (int64_t)P * P;
   gram_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_partial, pl.n_tiles, pl.n_pairs,
                                                                           pl.n_splits, P, d_C, ldc);
   if (launches) *launches += 3;
+  return nullptr;
+}
+
+// The same build with X still in (pinned) host memory: the matrix crosses PCIe one block of
+// TILE columns at a time on `copy_stream`, and as soon as block b is there `stream` runs its
+// column sums, centres it in place and multiplies the tile pairs (i <= b, b).  Only the pairs of
+// the last block (2 / (n_tiles + 1) of the work) are left when the copy ends.  Every partial
+// tile is the same launch-independent computation, so the result has the bits of gram_build.
+const char* gram_build_from_host(const double* hX, int n_samples, int P, double* dXc, int64_t ld_centered,
+                                 double* d_partial, const GramPlan& pl, double* d_colsum, double* d_mean,
+                                 double* d_C, int64_t ldc, double* d_scratch_part, int* d_error_flag,
+                                 cudaStream_t stream, cudaStream_t copy_stream, cudaEvent_t* block_arrived,
+                                 int64_t* launches) {
+  encode_fn_t enc = get_encode_fn();
+  if (!enc) return "cuTensorMapEncodeTiled entry point not available";
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {(cuuint64_t)n_samples, (cuuint64_t)P};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld_centered * 8};
+  cuuint32_t box[2] = {BOX_K, TILE};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)dXc, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed";
+  if (cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM) !=
+      cudaSuccess)
+    return "cudaFuncSetAttribute(gram_dmma_kernel) failed";
+  cudaMemsetAsync(d_error_flag, 0, sizeof(int), stream);
+  int chunks = (int)((n_samples + 65535) / 65536);
+  if (chunks < 1) chunks = 1;
+  if (chunks > GRAM_MEAN_MAX_CHUNKS) chunks = GRAM_MEAN_MAX_CHUNKS;
+  int gx = (int)((ld_centered + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  for (int b = 0; b < pl.n_tiles; b++) {
+    const int c0 = b * TILE;
+    const int nc = (P - c0 < TILE) ? P - c0 : TILE;
+    double* dst = dXc + (int64_t)c0 * ld_centered;
+    const double* src = hX + (int64_t)c0 * n_samples;
+    cudaError_t e;
+    if (ld_centered == n_samples)
+      e = cudaMemcpyAsync(dst, src, (size_t)n_samples * nc * 8, cudaMemcpyHostToDevice, copy_stream);
+    else
+      e = cudaMemcpy2DAsync(dst, (size_t)ld_centered * 8, src, (size_t)n_samples * 8, (size_t)n_samples * 8,
+                            (size_t)nc, cudaMemcpyHostToDevice, copy_stream);
+    if (e != cudaSuccess) return "H2D copy of a column block failed";
+    cudaEventRecord(block_arrived[b], copy_stream);
+    cudaStreamWaitEvent(stream, block_arrived[b], 0);
+    column_sum_partial_kernel<<<dim3(nc, chunks), 256, 0, stream>>>(dst, ld_centered, n_samples, chunks,
+                                                                     d_scratch_part + (int64_t)c0 * chunks);
+    column_mean_finish_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(d_scratch_part + (int64_t)c0 * chunks, chunks,
+                                                                     nc, n_samples, d_colsum + c0, d_mean + c0);
+    center_kernel<<<dim3(gx, nc), 256, 0, stream>>>(dst, ld_centered, n_samples, d_mean + c0, dst, ld_centered);
+    gram_dmma_kernel<<<(unsigned)(pl.n_splits * (b + 1)), GRAM_THREADS, GRAM_SMEM, stream>>>(
+        tmap, pl.n_tiles, pl.n_pairs, pl.stages_total, pl.n_splits, d_partial, d_error_flag, b);
+    if (launches) *launches += 4;
+  }
+  const int64_t total = (int64_t)P * P;
+  gram_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(d_partial, pl.n_tiles, pl.n_pairs,
+                                                                          pl.n_splits, P, d_C, ldc);
+  if (launches) *launches += 1;
   return nullptr;
 }
 

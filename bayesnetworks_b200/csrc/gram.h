@@ -31,4 +31,12 @@ const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, doub
                        double* d_mean, double* d_C, int64_t ldc, double* d_scratch_part,
                        int* d_error_flag, cudaStream_t stream, int64_t* launches, bool mean_given = false);
 
+// X in (pinned) host memory, column-major n_samples x P: the H2D copy is pipelined with the
+// build, one block of 128 columns at a time; block_arrived: pl.n_tiles events.  Same bits.
+const char* gram_build_from_host(const double* hX, int n_samples, int P, double* dXc, int64_t ld_centered,
+                                 double* d_partial, const GramPlan& pl, double* d_colsum, double* d_mean,
+                                 double* d_C, int64_t ldc, double* d_scratch_part, int* d_error_flag,
+                                 cudaStream_t stream, cudaStream_t copy_stream, cudaEvent_t* block_arrived,
+                                 int64_t* launches);
+
 }  // namespace bn
