@@ -105,6 +105,7 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int windows;
   int need_full;       // the last round could not start: top the ring up completely before retrying
   int anc_changed;     // the last accepted move changed ancestor rows (else no cycle bit can differ)
+  int64_t next_log;    // a multiple of output_every that no logged iteration before s.iter precedes
   int status;
 };
 
@@ -692,7 +693,7 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   for (int t = 0; t < 3; t++) { s.proposed[t] = 0; s.reject[t] = 0; }
   s.n_rows = 0; s.n_moves = 0; s.valid_iters = 0; s.alg_bytes = 0;
   s.gll_ok = 0; s.gll = 0.0;
-  s.win = 4; s.windows = 0; s.status = 0; s.need_full = 0;
+  s.win = 4; s.windows = 0; s.status = 0; s.need_full = 0; s.anc_changed = 0; s.next_log = 0;
   for (int t = 0; t < 6; t++) s.cyc[t] = 0;
   s.slots_sim = 0;
 }
@@ -1278,8 +1279,10 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     Warp::sync();
     anc_after_delete(p, m, c, s.anc_changed);
   }
-  if (m.dscore)  // the deletion scores of c are no longer valid
-    for (int e = l; e < MP; e += Warp::NL) m.dscore[(int64_t)c * MP + e] = nan_sentinel();
+  if (m.dscore) {  // the deletion scores of c are no longer valid
+    double* dc = m.dscore + (uint32_t)c * (uint32_t)MP;
+    for (int e = l; e < MP; e += Warp::NL) dc[e] = nan_sentinel();
+  }
   if (s.n_moves < p.moves_capacity) {
     if (l == 0) {
       int* mv = m.moves + (int64_t)s.n_moves * 4;
@@ -1407,7 +1410,11 @@ BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const 
   const uint32_t m_p2 = Warp::ballot(counted && type == 2);
   const uint32_t m_r1 = m_p1 & ~accbit, m_r2 = m_p2 & ~accbit;
   const uint32_t m_npd = Warp::ballot(valid && (rec & REC_NPD));
-  const uint32_t m_log = Warp::ballot(valid && (it % p.output_every == 0));  // :63-65
+  // logged iterations (i % output == 0, :63-65): at most one per epoch when output >= the epoch
+  // length, found by comparing with the next multiple instead of a division per lane
+  while (s.next_log < s.iter) s.next_log += p.output_every;  // warp-uniform, rarely more than one step
+  const bool logged = (p.output_every >= WIN) ? (it == (int)s.next_log) : (it % p.output_every == 0);
+  const uint32_t m_log = Warp::ballot(valid && logged);
   const int kk = valid ? (rec >> REC_KK_SHIFT) : 0;
   const int bytes = Warp::sum(valid ? 4 * (kk + 1) * (kk + 2) + 8 : 0);
   // members left by the last LogPrior(): the proposed graph for valid iterations
