@@ -294,8 +294,9 @@ def run_ours(a):
                 "note": "latency-bound sequential chains (dependent instruction stream, see "
                         "profiles/r01_chain_kernel.md): algorithmic gather bytes = sum over scored proposals of "
                         "8*(k'+1)(k'+2)/2+8 (SURVEY.md 8d); the Gram (8 MB) is L2 resident, so DRAM traffic "
-                        "(`traffic`, bytes per launch, ncu) is far BELOW the algorithmic bytes; the HBM-bound "
-                        "scoring kernel of this path is kernels.sweep"}
+                        "(`traffic`, bytes per launch, ncu) is far BELOW the algorithmic bytes; ncu: 0.73 warp-"
+                        "instructions per cycle per active SM, dominant stall = fixed-latency dependences; "
+                        "the HBM-bound scoring kernel of this path is kernels.sweep"}
 
     line = {"metric": METRIC, "value": proposals / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
