@@ -923,12 +923,19 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
     }
     const int kc = ovf ? 0 : m.npar[c];
     const int* pc = m.par + (int64_t)c * MP;
+    Par8 pc8;
+    if (MP <= 8) pc8 = load_par8(p, m, c);
     for (;;) {
       BN_UAT(u);
       j = (int)(P * u);
       if (ovf) break;
       int ok = (p.node_type[j] != 2 && j != c);
-      for (int t = 0; t < kc; t++) if (pc[t] == j) ok = 0;
+      if (MP <= 8) {  // unused slots hold -1
+#pragma unroll
+        for (int t = 0; t < 8; t++) if (pc8.q[t] == j) ok = 0;
+      } else {
+        for (int t = 0; t < kc; t++) if (pc[t] == j) ok = 0;
+      }
       if (ok) break;
     }
     // CheckValidity -> pathExists (src/network.h:366-432): is c an ancestor of j?
@@ -949,10 +956,9 @@ BN_HD void replay_position(const ChainParams& p, const ChainMem& m, int n_haspar
 #undef BN_UAT
   // the acceptance uniform must be in the ring as well, and the count (+1) must fit the record
   if (i >= hi || i - q >= REC_LEN_MASK) ovf = 1;
-  const int ag = (!ovf && p.sim_edge[(int64_t)j + (int64_t)c * P]) ? 1 : 0;
   ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e; ws.t_full[slot] = full;
   ws.t_rec[slot] = (int)(i - q) | (type == 2 ? REC_TYPE : 0) | (cyc ? REC_CYC : 0) | (ovf ? REC_OVF : 0) |
-                   (ag ? REC_AG : 0) | (many ? REC_FULLMANY : 0);
+                   (many ? REC_FULLMANY : 0);  // (REC_AG: build_record)
 }
 
 // what the walk needs of a (consumable) record: an addition sets `valid` itself
@@ -1026,14 +1032,18 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
     decide_record(p, m, rc, ubuf, ws, slot);
     return;
   }
-  ws.t_lu[slot] = log(ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)]);
   int kk = 0, npd = 0;
   double sc;
   // the score of a deletion is a function of (child, slot) until the child's parents change:
   // it is kept in a per-chain table (L2), which takes half of the records off the sub-Gram
-  // gather -- the throughput limit of this phase (one L1TEX wavefront per gathered entry)
-  double* cache = (m.dscore && (rec & REC_TYPE)) ? m.dscore + (int64_t)ws.t_c[slot] * p.max_par + ws.t_e[slot] : nullptr;
+  // gather -- the throughput limit of this phase (one L1TEX wavefront per gathered entry).
+  // The two L2 reads of the record (that table, the prior adjacency) are issued first and the
+  // logarithm of the acceptance uniform is taken while they are in flight.
+  const int rc_c = ws.t_c[slot], rc_j = ws.t_j[slot];
+  double* cache = (m.dscore && (rec & REC_TYPE)) ? m.dscore + (uint32_t)rc_c * (uint32_t)p.max_par + ws.t_e[slot] : nullptr;
   const double cached = cache ? ld_shared_ro(cache) : nan_sentinel();
+  const int ag = ld_shared_ro(p.sim_edge + (int64_t)rc_j + (int64_t)rc_c * p.P) ? REC_AG : 0;
+  ws.t_lu[slot] = log(ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)]);
   if (cached == cached) {
     sc = cached;
     kk = m.npar[ws.t_c[slot]] - 1;
@@ -1043,7 +1053,7 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
     if (cache) *cache = sc;  // (duplicates within a round store the same value)
   }
   ws.t_score[slot] = sc;
-  ws.t_rec[slot] = rec | (npd ? REC_NPD : 0) | (kk << REC_KK_SHIFT);
+  ws.t_rec[slot] = rec | ag | (npd ? REC_NPD : 0) | (kk << REC_KK_SHIFT);
   decide_record(p, m, rc, ubuf, ws, slot);
 }
 
