@@ -66,6 +66,8 @@ struct ChainParams {  // read-only, shared by all chains of a run
   // prior graph (InitialNetwork == 0 start), [P][max_par] + [P]
   const int* prior_par;
   const int* prior_npar;
+  // row geometry of the ancestor bitsets for this warp width (set_row_geom)
+  int g_chunks, g_lpr, g_rpp;
 };
 
 struct ChainMem {  // per-chain global memory
@@ -201,12 +203,16 @@ BN_HD U4 with_bit(U4 v, int b) {  // set bit b (0..127) of the chunk
 }
 
 struct RowGeom { int chunks, lpr, rpp; };
+// computed once per chain (the device and the one-lane host build differ in Warp::NL)
+BN_HD void set_row_geom(ChainParams& p) {
+  p.g_chunks = (p.W + 3) / 4;
+  p.g_lpr = 1;
+  while (p.g_lpr < p.g_chunks && p.g_lpr < Warp::NL) p.g_lpr <<= 1;
+  p.g_rpp = Warp::NL / p.g_lpr;
+}
 BN_HD RowGeom row_geom(const ChainParams& p) {
   RowGeom g;
-  g.chunks = (p.W + 3) / 4;
-  g.lpr = 1;
-  while (g.lpr < g.chunks && g.lpr < Warp::NL) g.lpr <<= 1;
-  g.rpp = Warp::NL / g.lpr;
+  g.chunks = p.g_chunks; g.lpr = p.g_lpr; g.rpp = p.g_rpp;
   return g;
 }
 

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
     rng_init_replay(rng, ra.replay + (int64_t)ch * ra.replay_len, ra.replay_len, ubuf);
 
   ChainParams pp = p;
+  set_row_geom(pp);
   if (!m.moves) pp.moves_capacity = 0;
   if (ALL_SMEM || sm.off_types >= 0) {
     uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);

@@ -28,6 +28,7 @@ extern "C" int emu_run_chain(
   p.initial_network = initial_network; p.drop = drop; p.n_iter = n_iter;
   p.output_every = output_every; p.trace_capacity = capacity; p.moves_capacity = moves_capacity;
   p.prior_par = prior_par; p.prior_npar = prior_npar;
+  set_row_geom(p);
 
   std::vector<int> par((size_t)P * max_par), npar(P), born((size_t)P * max_par);
   std::vector<int> scratch((size_t)scratch_words(P, 1, 1)), hp_list(P);
