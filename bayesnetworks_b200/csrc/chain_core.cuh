@@ -679,17 +679,17 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   for (int c = l; c < P; c += Warp::NL) {
     const int k = m.npar[c];
     int npd = 0;
-    if constexpr (KMAX <= 8) {
+    // the score does not depend on MaxPar: sets of up to 8 parents take the register-resident
+    // scorer whatever the limit is (MaxPar = 50 is the R default; real parent sets are small)
+    if (KMAX <= 8 || k <= 8) {
       Parents8 S;
 #pragma unroll
       for (int e = 0; e < 8; e++) S.s[e] = (e < k) ? m.par[(int64_t)c * MP + e] : c;
       m.base[c] = score_set8(p.C, p.ldc, c, S, k, p.n_samples);
       npd = (m.base[c] == -INFINITY) ? 1 : 0;
-    } else {
-      double L[KMAX * (KMAX + 1) / 2], z[KMAX];
-      int S[KMAX];
-      for (int e = 0; e < k; e++) S[e] = m.par[(int64_t)c * MP + e];
-      m.base[c] = score_set(p.C, p.ldc, c, S, k, p.n_samples, L, z, &npd);
+    } else if constexpr (KMAX > 8) {
+      int kk = 0;
+      m.base[c] = score_set_big<KMAX>(p.C, p.ldc, c, m.par + (int64_t)c * MP, k, 0, 0, 0, p.n_samples, &kk, &npd);
     }
   }
   Warp::sync();
@@ -804,8 +804,8 @@ BN_HD double score_proposal(const ChainParams& p, const ChainMem& m, int type, i
   const int* pc = m.par + (int64_t)c * p.max_par;
   const int k = m.npar[c];
   int kk = 0;
-  double nw;
-  if constexpr (KMAX <= 8) {
+  double nw = 0.0;
+  if (KMAX <= 8 || k + (type == 1 ? 1 : -1) <= 8) {  // (chain_init: small sets use the K = 8 scorer)
     Parents8 S;
     if (type == 1) {
       kk = k + 1;
@@ -821,16 +821,8 @@ BN_HD double score_proposal(const ChainParams& p, const ChainMem& m, int type, i
     }
     nw = score_set8(p.C, p.ldc, c, S, kk, p.n_samples);
     *npd = (nw == -INFINITY) ? 1 : 0;
-  } else {
-    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
-    int S[KMAX];
-    if (type == 1) {
-      for (int e = 0; e < k; e++) S[kk++] = pc[e];
-      S[kk++] = j;
-    } else {
-      for (int e = 0; e < k; e++) if (e != del) S[kk++] = pc[e];
-    }
-    nw = score_set(p.C, p.ldc, c, S, kk, p.n_samples, L, z, npd);
+  } else if constexpr (KMAX > 8) {
+    nw = score_set_big<KMAX>(p.C, p.ldc, c, pc, k, type, j, del, p.n_samples, &kk, npd);
   }
   *kk_out = kk;
   return nw;

@@ -135,4 +135,26 @@ double score_set8(const double* C, int64_t ldc, int c, Parents8 S, int k, int n_
   return score_set_small<8>(C, ldc, c, S.s, k, n_samples, &npd);  // -inf <=> not positive definite
 }
 
+// Parent sets of more than 8 nodes (possible when MaxPar > 8): the factor does not fit in
+// registers.  A function of its own so that its local arrays (16 KB at KMAX = 64) are a frame
+// that exists during the call only, not part of every thread's frame in the chain kernel.
+// type 1: parents pc[0..k) plus j; type 2: pc[0..k) without slot del; type 0: pc[0..k) as is.
+template <int KMAX>
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+double score_set_big(const double* C, int64_t ldc, int c, const int* pc, int k, int type, int j, int del,
+                     int n_samples, int* kk_out, int* nonpd) {
+  double L[KMAX * (KMAX + 1) / 2], z[KMAX];
+  int S[KMAX];
+  int kk = 0;
+  for (int e = 0; e < k; e++)
+    if (type != 2 || e != del) S[kk++] = pc[e];
+  if (type == 1) S[kk++] = j;
+  *kk_out = kk;
+  return score_set(C, ldc, c, S, kk, n_samples, L, z, nonpd);
+}
+
 }  // namespace bn
