@@ -1389,16 +1389,19 @@ BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const 
   while (n < want) {
     const int w = ws.t_walk[k];
     const int f = w >> (16 + v);  // bit 0 outgoing valid, bit 2 accepted, bit 4 stop mark
-    if (f & 0x14) {
+    if (f & 0x14) {               // rare: the common path has this one branch besides the counter
       if (f & 0x10) { *stop = w; break; }
-      acc = 1;
+      if (l == n) { myk = k; myvalid = 1; }  // an accepted iteration is a valid one
+      acc = 1; k_acc = k;
+      k += (w >> (v << 3)) & 0xff;
+      v = 1;
+      n++;
+      break;
     }
     if (l == n) { myk = k; myvalid = f & 1; }
-    k_acc = k;
     k += (w >> (v << 3)) & 0xff;
     v = f & 1;
     n++;
-    if (acc) break;
   }
   *accepted = acc;
   if (n == 0) return 0;
