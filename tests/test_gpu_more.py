@@ -68,6 +68,7 @@ def test_config3_shape_vs_oracle(oracle):
     with Context.from_data(X, g.source, g.target, nt, max_par=8) as ctx:
         r = ctx.run(n_iter=6000, output=100, rng="wh", log_moves=True)[0][0]
         _same_trace(r, ref, 10000)
+        assert r.n_nonpd == 0 and ref.n_nonpd == 0   # BASELINE config 3 shape
         # per-node scores of the final graph against the reference-order scoring
         want = oracle.score_graph(X, r.final_parents, r.final_npar)
         got = ctx.score_nodes(np.arange(100), r.final_parents, r.final_npar)
@@ -247,6 +248,7 @@ def test_full_size_properties():
             assert abs(C[a, b] - want) <= 1e-9 * N
         seeds = chain_seeds(6)
         r6, _ = ctx.run(n_chains=6, n_iter=4000, output=100, rng="wh", seeds=seeds)
+        assert all(r.n_nonpd == 0 for r in r6)   # BASELINE config 4: no degenerate parent Gram
         r2, _ = ctx.run(n_chains=2, n_iter=4000, output=100, rng="wh", seeds=seeds[4:6])
         for a, b in ((r6[4], r2[0]), (r6[5], r2[1])):
             for k in INT_COLS:

@@ -77,6 +77,7 @@ def test_chain_bit_identical_to_reference(ctx, golden, name, rng, seed):
     assert np.array_equal(np.asarray(r.edges(), np.int32), golden[f"{name}_final_edges"])
     assert list(r.proposed) == list(golden[f"{name}_proposed"])
     assert list(r.reject) == list(golden[f"{name}_reject"])
+    assert r.n_nonpd == 0   # BASELINE configs 1 / 2(i): no degenerate parent Gram (DESIGN.md deviations)
 
 
 def test_chain_every_iteration(dataset, golden):
