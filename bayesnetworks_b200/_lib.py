@@ -47,14 +47,15 @@ class ChainStats(C.Structure):
     _fields_ = [("uniforms", C.c_int64), ("valid_iters", C.c_int64), ("proposed", C.c_int * 3),
                 ("reject", C.c_int * 3), ("n_nonpd", C.c_int), ("total_edges", C.c_int),
                 ("status", C.c_int), ("windows", C.c_int), ("alg_bytes", C.c_int64),
-                ("phase_cycles", C.c_int64 * 6), ("slots_simulated", C.c_int64)]
+                ("phase_cycles", C.c_int64 * 6), ("slots_simulated", C.c_int64), ("kernel_cycles", C.c_int64)]
 
 
 import numpy as _np
 CHAIN_STATS_DTYPE = _np.dtype([("uniforms", "<i8"), ("valid_iters", "<i8"), ("proposed", "<i4", (3,)),
                                ("reject", "<i4", (3,)), ("n_nonpd", "<i4"), ("total_edges", "<i4"),
                                ("status", "<i4"), ("windows", "<i4"), ("alg_bytes", "<i8"),
-                               ("phase_cycles", "<i8", (6,)), ("slots_simulated", "<i8")], align=True)
+                               ("phase_cycles", "<i8", (6,)), ("slots_simulated", "<i8"), ("kernel_cycles", "<i8")],
+                              align=True)
 assert CHAIN_STATS_DTYPE.itemsize == C.sizeof(ChainStats)
 
 
@@ -63,7 +64,7 @@ class RunArgs(C.Structure):
                 ("replay_len", C.c_int64), ("initial_network", C.c_int), ("drop", C.c_int),
                 ("n_iter", C.c_int), ("output_every", C.c_int), ("device_outputs", C.c_int),
                 ("moves_capacity", C.c_int), ("n_moves", _ip), ("moves", _ip), ("edge_freq", _ip),
-                ("npar_freq", _ip)]
+                ("npar_freq", _ip), ("mt_state_in", _ip), ("mt_state_out", _ip)]
 
 
 _lib = None
@@ -108,7 +109,7 @@ def lib() -> C.CDLL:
                          C.c_void_p, C.POINTER(C.c_float)]
     L.bn_main_fun.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
-                               C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 8)
+                               C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 10)
     _lib = L
     return L
 

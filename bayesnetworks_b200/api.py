@@ -45,11 +45,18 @@ class ChainResult:
     accepted_moves: Optional[np.ndarray] = None  # rows (iter, movetype, child, parent)
     edge_freq: Optional[np.ndarray] = None       # [child, parent] counts (posterior tabulation)
     npar_freq: Optional[np.ndarray] = None       # [node, k] iterations spent with k parents
+    kernel_cycles: int = 0                       # SM cycles of the chain, first to last iteration
+    mt_state: Optional[np.ndarray] = None        # R-MT stream state after the run (.Random.seed[2:626])
 
     def edges(self):
         """(parent, child) pairs, 0-based, per-child list order."""
         return [(int(self.final_parents[c, e]), c)
                 for c in range(len(self.final_npar)) for e in range(int(self.final_npar[c]))]
+
+
+def _i32_bits(a) -> np.ndarray:
+    """Integers as 32-bit patterns (R stores the Mersenne-Twister words as signed ints)."""
+    return np.ascontiguousarray((np.asarray(a).astype(np.int64) & 0xFFFFFFFF).astype(np.uint32).view(np.int32))
 
 
 def set_default_stream(cuda_stream: Optional[int]) -> None:
@@ -204,8 +211,13 @@ class Context:
 
     # -- chains --------------------------------------------------------------
     def run(self, n_chains=1, n_iter=1000, output=100, initial_network=2, drop=0, rng="wh",
-            seeds=None, replay=None, log_moves=False, moves_capacity=None, tabulate=False):
-        """Run ``n_chains`` independent chains; returns (list[ChainResult], kernel_ms)."""
+            seeds=None, replay=None, log_moves=False, moves_capacity=None, tabulate=False,
+            mt_state=None, want_mt_state=False):
+        """Run ``n_chains`` independent chains; returns (list[ChainResult], kernel_ms).
+
+        ``mt_state`` (rng="rmt"): R's stream state per chain, ``.Random.seed[2:626]`` (625 ints:
+        position + 624 words), instead of ``set.seed(seeds)``; ``want_mt_state`` returns the
+        state after the run in ``ChainResult.mt_state``."""
         L = _lib.lib()
         kind = _RNG_KINDS[rng]
         p, mp = self.n_nodes, self.max_par
@@ -242,6 +254,13 @@ class Context:
                 raise ValueError("replay must be (n_chains, replay_len)")
             args.replay = rp.ctypes.data_as(_lib._dp)
             args.replay_len = rp.shape[1]
+        mt_in = mt_out = None
+        if mt_state is not None:
+            mt_in = _i32_bits(mt_state).reshape(n_chains, 625)
+            args.mt_state_in = mt_in.ctypes.data_as(_lib._ip)
+        if want_mt_state or mt_state is not None:
+            mt_out = np.zeros((n_chains, 625), dtype=np.int32)
+            args.mt_state_out = mt_out.ctypes.data_as(_lib._ip)
         args.initial_network, args.drop = int(initial_network), int(drop)
         args.n_iter, args.output_every, args.device_outputs = int(n_iter), int(output), 0
         moves = n_moves = None
@@ -280,7 +299,8 @@ class Context:
                 proposed=tuple(s["proposed"].tolist()), reject=tuple(s["reject"].tolist()), n_nonpd=int(s["n_nonpd"]),
                 total_edges=int(s["total_edges"]), windows=int(s["windows"]), alg_bytes=int(s["alg_bytes"]),
                 phase_cycles=tuple(s["phase_cycles"].tolist()),
-                slots_simulated=int(s["slots_simulated"]),
+                slots_simulated=int(s["slots_simulated"]), kernel_cycles=int(s["kernel_cycles"]),
+                mt_state=None if mt_out is None else mt_out[ch],
                 final_parents=fpar[ch],
                 final_npar=fnpar[ch],
                 accepted_moves=None if moves is None else moves[ch, :int(n_moves[ch])],
@@ -310,12 +330,15 @@ def block_gram_device(data_ptr, ld, n_rows, n_nodes, mean_ptr, out_ptr, device=0
 def main_fun(X, graph_source: Sequence[int], graph_target: Sequence[int],
              graph_node_labels: Sequence[int], graph_node_type: Sequence[int], MaxPar: int = 50,
              phi: float = 1, omega: float = 6.9, InitialNetwork: int = 2, drop: int = 0,
-             N: int = 1000, output: int = 10, *, rng="wh", seed=None) -> dict:
+             N: int = 1000, output: int = 10, *, rng="wh", seed=None, random_seed=None) -> dict:
     """``main_fun`` of ``src/bayesnet_mcmc.cpp:27-38`` through the C ABI (``bn_main_fun``).
 
     ``rng``/``seed`` choose the uniform stream that stands in for ``R::runif``:
     ``"wh"`` (Wichmann-Hill, ``seed`` = (ix, iy, iz) or None for the reference's
     10437/13568/30524) or ``"rmt"`` (R's Mersenne-Twister, ``seed`` as in ``set.seed``).
+    ``random_seed``: R's ``.Random.seed`` (626 ints, Mersenne-Twister kind 10403) as the reference
+    finds it on entry (``Rcpp::RNGScope``, ``src/RcppExports.cpp:13``); the state it would leave
+    behind is returned under the key ``".Random.seed"``.
     Returns the eight result columns as arrays, in the reference's order.
     """
     Xf = np.asfortranarray(np.asarray(X, dtype=np.float64))
@@ -330,24 +353,36 @@ def main_fun(X, graph_source: Sequence[int], graph_target: Sequence[int],
         sd = np.zeros(3, dtype=np.int32)
         s_in = np.atleast_1d(np.asarray(seed, dtype=np.int64))
         sd[:len(s_in)] = s_in
-    elif kind == BN_RNG_RMT:
-        raise ValueError("rng='rmt' needs seed= (the value given to set.seed)")
+    st_in = st_out = None
+    if random_seed is not None:
+        rs = np.asarray(random_seed, dtype=np.int64)
+        if rs.shape != (626,) or rs[0] % 100 != 3:
+            raise ValueError("random_seed must be R's .Random.seed of the Mersenne-Twister (626 ints, kind %%100 == 3)")
+        kind = BN_RNG_RMT
+        st_in = _i32_bits(rs[1:])
+        st_out = np.zeros(625, dtype=np.int32)
+    elif kind == BN_RNG_RMT and seed is None:
+        raise ValueError("rng='rmt' needs seed= (the value given to set.seed) or random_seed=")
     cap = max(1, (int(N) + int(output) - 1) // int(output)) if output > 0 else 1
     cols = {k: np.zeros(cap, dtype=np.float64 if k == "globalLL" else np.int32) for k in TRACE_COLUMNS}
     rows = _lib.lib().bn_main_fun(ptr(Xf), n, p, ptr(src), ptr(tgt), len(src), ptr(labels), ptr(nt),
                                   int(MaxPar), float(phi), float(omega), int(InitialNetwork),
                                   int(drop), int(N), int(output), int(kind), ptr(sd), cap,
-                                  *[ptr(cols[k]) for k in TRACE_COLUMNS])
+                                  *[ptr(cols[k]) for k in TRACE_COLUMNS], ptr(st_in), ptr(st_out))
     if rows < 0:
         raise BnError(-rows, _lib.lib().bn_last_error().decode("utf-8", "replace"))
-    return {k: cols[k][:rows].copy() for k in TRACE_COLUMNS}
+    out = {k: cols[k][:rows].copy() for k in TRACE_COLUMNS}
+    if st_out is not None:
+        out[".Random.seed"] = np.concatenate([[int(np.asarray(random_seed)[0])], st_out]).astype(np.int32)
+    return out
 
 
 def bn_mcmc(X, graph: Network, MaxPar: int = 50, phi: float = 1, omega: float = 6.9,
             InitialNetwork: int = 2, drop: int = 0, N: int = 1000, output: int = 100, *,
-            rng="wh", seed=None) -> dict:
+            rng="wh", seed=None, random_seed=None) -> dict:
     """``bn_mcmc`` of ``R/bn_mcmc.R:8-25``: unpack the network object and forward to main_fun."""
     return main_fun(X=X, graph_target=graph.target, graph_source=graph.source,
                     graph_node_labels=np.arange(graph.n_nodes, dtype=np.int32),
                     graph_node_type=graph.node_type_codes(), MaxPar=MaxPar, phi=phi, omega=omega,
-                    InitialNetwork=InitialNetwork, drop=drop, N=N, output=output, rng=rng, seed=seed)
+                    InitialNetwork=InitialNetwork, drop=drop, N=N, output=output, rng=rng, seed=seed,
+                    random_seed=random_seed)

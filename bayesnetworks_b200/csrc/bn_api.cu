@@ -159,8 +159,9 @@ struct bn_ctx {
   double* d_colsum = nullptr;  // [P]
   uint8_t* d_node_type = nullptr;
   uint8_t* d_sim_edge = nullptr;  // [parent + child*P]
-  int* d_prior_par = nullptr;     // [P][max_par]
+  int* d_prior_par = nullptr;     // [P][prior_stride]
   int* d_prior_npar = nullptr;    // [P]
+  int prior_stride = 1;           // largest in-degree of the supplied graph (>= 1)
   float gram_ms = 0.f;
   int64_t launches = 0;
   std::vector<void*> owned;  // device allocations freed by bn_destroy
@@ -223,15 +224,21 @@ static int ctx_begin(int n_samples, int P, const int* src, const int* tgt, int n
   tm.lap("stream create");
   c->stream = g_default_stream ? g_default_stream : c->own_stream;
 
-  // parent lists edges[tgt-1].push_back(src-1), src/network.h:117-120
-  std::vector<int> par((size_t)P * max_par, -1), npar(P, 0);
+  // parent lists edges[tgt-1].push_back(src-1), src/network.h:117-120.  The supplied graph may
+  // give a node more than max_par parents: with InitialNetwork = 2 (the default) it only feeds
+  // simEdge / NsimEdges (:138-146,164-169), so the lists keep their own stride and the limit is
+  // checked by bn_run for InitialNetwork = 0 only.
+  std::vector<int> npar(P, 0);
+  for (int e = 0; e < n_edges; e++) npar[tgt[e] - 1]++;
+  int stride = 1;
+  for (int p = 0; p < P; p++) if (npar[p] > stride) stride = npar[p];
+  c->prior_stride = stride;
+  std::fill(npar.begin(), npar.end(), 0);
+  std::vector<int> par((size_t)P * stride, -1);
   std::vector<uint8_t> sim((size_t)P * P, 0), types(P);
   for (int e = 0; e < n_edges; e++) {
     const int child = tgt[e] - 1, parent = src[e] - 1;
-    if (npar[child] >= max_par) {
-      return fail(BN_ERR_BAD_ARG, "node %d has more than max_par=%d parents in the supplied graph", child, max_par);
-    }
-    par[(size_t)child * max_par + npar[child]++] = parent;
+    par[(size_t)child * stride + npar[child]++] = parent;
     // simEdge(parent, child) = 1; NsimEdges counts list entries, src/network.h:140-145
     sim[(size_t)parent + (size_t)child * P] = 1;
     c->n_sim_edges++;
@@ -648,6 +655,33 @@ static void rmt_seed_state(uint32_t seed, uint32_t* mt) {
   }
 }
 
+// R's MT_genrand state step (R sources, src/main/RNG.c): advance (mt, mti) by n_draws uniforms.
+// Bookkeeping of the stream position for mt_state_out only -- the uniforms themselves are
+// generated on the device (rng_core.cuh).
+static void rmt_advance(uint32_t* mt, int& mti, int64_t n_draws) {
+  const int N = 624, M = 397;
+  const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MAG = 0x9908b0dfu;
+  while (n_draws > 0) {
+    if (mti >= N) {
+      int kk = 0;
+      for (; kk < N - M; kk++) {
+        const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+      }
+      for (; kk < N - 1; kk++) {
+        const uint32_t y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+      }
+      const uint32_t y = (mt[N - 1] & UPPER) | (mt[0] & LOWER);
+      mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
+      mti = 0;
+    }
+    const int64_t take = n_draws < (int64_t)(N - mti) ? n_draws : (int64_t)(N - mti);
+    mti += (int)take;
+    n_draws -= take;
+  }
+}
+
 struct DevBuf {  // frees on scope exit
   std::vector<void*> ptrs;
   ~DevBuf() { for (void* p : ptrs) pool_free(p); }
@@ -665,9 +699,14 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   const int nc = a->n_chains;
   if (nc <= 0) return fail(BN_ERR_BAD_ARG, "n_chains <= 0");
   if (a->n_iter < 0 || a->output_every <= 0 || a->drop < 0) return fail(BN_ERR_BAD_ARG, "bad n_iter/output/drop");
-  if (a->initial_network == 1)
-    return fail(BN_ERR_UNSUPPORTED, "InitialNetwork=1 (random start) is undefined behaviour in the reference (src/network.h:151-157)");
-  if (a->initial_network != 0 && a->initial_network != 2) return fail(BN_ERR_BAD_ARG, "InitialNetwork must be 0 or 2");
+  // InitialNetwork: 1 = random start, 2 = empty graph, anything else keeps the supplied graph
+  // (src/network.h:148-170)
+  const int init_net = (a->initial_network == 1 || a->initial_network == 2) ? a->initial_network : 0;
+  if (init_net == 0 && c->prior_stride > c->max_par)
+    return fail(BN_ERR_BAD_ARG, "InitialNetwork=%d starts from the supplied graph, in which a node has %d parents (max_par=%d)",
+                a->initial_network, c->prior_stride, c->max_par);
+  if (a->mt_state_in && a->rng_kind != BN_RNG_RMT) return fail(BN_ERR_BAD_ARG, "mt_state_in needs rng_kind = BN_RNG_RMT");
+  if (a->mt_state_out && a->rng_kind != BN_RNG_RMT) return fail(BN_ERR_BAD_ARG, "mt_state_out needs rng_kind = BN_RNG_RMT");
   if (a->rng_kind < BN_RNG_WH || a->rng_kind > BN_RNG_REPLAY) return fail(BN_ERR_BAD_ARG, "bad rng_kind");
   if (a->rng_kind == BN_RNG_REPLAY && (!a->replay || a->replay_len <= 0)) return fail(BN_ERR_BAD_ARG, "replay buffer missing");
   const int need = (a->n_iter + a->output_every - 1) / a->output_every;
@@ -675,7 +714,6 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   if (!trace->n_rows || !trace->iter || !trace->changed_node || !trace->movetype || !trace->global_ll ||
       !trace->additions || !trace->deletions || !trace->fn || !trace->fp)
     return fail(BN_ERR_BAD_ARG, "trace column pointer is NULL");
-  if (c->n_samples - c->max_par - 1 <= 0) return fail(BN_ERR_BAD_ARG, "n_samples <= max_par + 1");
   CU_TRY(cudaSetDevice(c->device));
 
   const int64_t P = c->P, MP = c->max_par, W = (P + 31) / 32;
@@ -694,6 +732,10 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   CU_TRY(buf.alloc(&w.hp_list, (size_t)(nc * P)));
   CU_TRY(buf.alloc(&w.scratch, (size_t)nc * w.scratch_n));
   CU_TRY(buf.alloc(&w.dscore, (size_t)(nc * P * MP)));
+  if (MP > 8) {  // per-node Cholesky factors + the candidate rows of a round (score_core.cuh)
+    CU_TRY(buf.alloc(&w.fac, (size_t)(nc * P * fac_stride(fac_mp((int)MP)))));
+    CU_TRY(buf.alloc(&w.rowbuf, (size_t)nc * REPLAY_POS * row_stride(fac_mp((int)MP))));
+  }
   CU_TRY(cudaMemsetAsync(w.dscore, 0xff, (size_t)(nc * P * MP) * sizeof(double), c->stream));  // NaN = unknown
   const bool dev_out = a->device_outputs != 0;
   if (dev_out) {
@@ -755,11 +797,26 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   CU_TRY(cudaMemcpyAsync(d_seeds, seeds.data(), seeds.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   ra.seeds = d_seeds;
   std::vector<uint32_t> mt;
+  std::vector<int> mt_pos;
   if (a->rng_kind == BN_RNG_RMT) {
     mt.resize((size_t)624 * nc);
-    for (int ch = 0; ch < nc; ch++) rmt_seed_state((uint32_t)seeds[3 * ch], &mt[(size_t)624 * ch]);
+    mt_pos.assign(nc, 624);  // set.seed() leaves the position at 624 = regenerate
+    for (int ch = 0; ch < nc; ch++) {
+      if (a->mt_state_in) {
+        // .Random.seed[2:626] of R: position (dummy[0]) + 624 state words
+        const int* st = a->mt_state_in + (size_t)625 * ch;
+        mt_pos[ch] = (st[0] < 0 || st[0] > 624) ? 624 : st[0];
+        for (int i = 0; i < 624; i++) mt[(size_t)624 * ch + i] = (uint32_t)st[1 + i];
+      } else {
+        rmt_seed_state((uint32_t)seeds[3 * ch], &mt[(size_t)624 * ch]);
+      }
+    }
+    int* d_pos = nullptr;
     CU_TRY(buf.alloc(&ra.mt_states, mt.size()));
+    CU_TRY(buf.alloc(&d_pos, (size_t)nc));
     CU_TRY(cudaMemcpyAsync(ra.mt_states, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(d_pos, mt_pos.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, c->stream));
+    ra.mt_pos = d_pos;
   }
   if (a->rng_kind == BN_RNG_REPLAY) {
     double* d_rep = nullptr;
@@ -771,11 +828,11 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
 
   ChainParams p;
   p.P = (int)P; p.max_par = (int)MP; p.W = (int)W; p.Ws = anc_stride((int)W); p.n_samples = c->n_samples;
-  p.C = c->d_C; p.ldc = P; p.node_type = c->d_node_type; p.sim_edge = c->d_sim_edge;
+  p.C = c->d_C; p.ldc = P; p.diag = c->d_diag; p.node_type = c->d_node_type; p.sim_edge = c->d_sim_edge;
   p.n_sim_edges = c->n_sim_edges; p.phi = c->phi; p.omega = c->omega;
-  p.initial_network = a->initial_network; p.drop = a->drop; p.n_iter = a->n_iter;
+  p.initial_network = init_net; p.drop = a->drop; p.n_iter = a->n_iter;
   p.output_every = a->output_every; p.trace_capacity = (int)cap; p.moves_capacity = mcap;
-  p.prior_par = c->d_prior_par; p.prior_npar = c->d_prior_npar;
+  p.prior_par = c->d_prior_par; p.prior_npar = c->d_prior_npar; p.prior_stride = c->prior_stride;
 
   ChainResult* d_res = nullptr;
   CU_TRY(buf.alloc(&d_res, (size_t)nc));
@@ -812,9 +869,22 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
       s.alg_bytes = res[ch].alg_bytes;
       for (int t = 0; t < 6; t++) s.phase_cycles[t] = res[ch].cyc[t];
       s.slots_simulated = res[ch].slots_sim;
+      s.kernel_cycles = res[ch].cyc_total;
     }
-    if (res[ch].status && !rc)
-      rc = fail(res[ch].status, "chain %d: no legal proposal within the uniform window (all candidate nodes are sources/full/sinks?)", ch);
+    if (res[ch].status == BN_ERR_NO_LEGAL_PROPOSAL && !rc)
+      rc = fail(res[ch].status, "chain %d: no legal proposal exists (every candidate child is a source or full, or every candidate parent a sink / already a parent)", ch);
+    if (a->rng_kind == BN_RNG_REPLAY && (res[ch].uniforms > a->replay_len || res[ch].status == BN_ERR_CAPACITY) && !rc)
+      rc = fail(BN_ERR_CAPACITY, "chain %d consumed %lld uniforms, the replay buffer holds %lld", ch,
+                (long long)res[ch].uniforms, (long long)a->replay_len);
+    if (a->mt_state_out && a->rng_kind == BN_RNG_RMT) {
+      // stream state after exactly the uniforms the chain consumed (.Random.seed[2:626] layout)
+      int pos = mt_pos[ch];
+      uint32_t* st = &mt[(size_t)624 * ch];
+      rmt_advance(st, pos, res[ch].uniforms);
+      int* out = a->mt_state_out + (size_t)625 * ch;
+      out[0] = pos;
+      for (int i = 0; i < 624; i++) out[1 + i] = (int)st[i];
+    }
   }
   const cudaMemcpyKind out_kind = dev_out ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost;
   CU_TRY(cudaMemcpy(trace->n_rows, nrows.data(), (size_t)nc * 4, out_kind));
@@ -848,7 +918,8 @@ extern "C" int bn_main_fun(const double* X, int n_samples, int n_nodes, const in
                            const int* graph_node_type, int MaxPar, double phi, double omega,
                            int InitialNetwork, int drop, int N, int output, int rng_kind, const int* seeds,
                            int capacity, int* iter, int* ChangedNode, int* movetype, double* globalLL,
-                           int* additions, int* deletions, int* FN, int* FP) {
+                           int* additions, int* deletions, int* FN, int* FP, const int* mt_state_in,
+                           int* mt_state_out) {
   (void)graph_node_labels;  // accepted and unused, as in the reference (src/bayesnet_mcmc.cpp:30,42-43)
   bn_ctx* c = nullptr;
   int rc = bn_create(X, n_samples, n_nodes, graph_source, graph_target, n_edges, graph_node_type, MaxPar, phi,
@@ -858,6 +929,7 @@ extern "C" int bn_main_fun(const double* X, int n_samples, int n_nodes, const in
   memset(&a, 0, sizeof(a));
   a.n_chains = 1; a.rng_kind = rng_kind; a.seeds = seeds; a.initial_network = InitialNetwork;
   a.drop = drop; a.n_iter = N; a.output_every = output;
+  a.mt_state_in = mt_state_in; a.mt_state_out = mt_state_out;
   int n_rows = 0;
   bn_trace t;
   t.capacity = capacity; t.n_rows = &n_rows; t.iter = iter; t.changed_node = ChangedNode; t.movetype = movetype;

@@ -87,6 +87,11 @@ struct Warp {
   static BN_D int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   static BN_D double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
   static BN_D int sum(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
+  static BN_D long long sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
   static BN_D int min(int v) { return __reduce_min_sync(0xffffffffu, v); }
   static BN_D int incl_scan(int v) {
     int l = lane();
@@ -111,6 +116,7 @@ struct Warp {
   static int shfl(int v, int) { return v; }
   static double shfl(double v, int) { return v; }
   static int sum(int v) { return v; }
+  static long long sum(long long v) { return v; }
   static int min(int v) { return v; }
   static int incl_scan(int v) { return v; }
   static double sum(double v) { return v; }

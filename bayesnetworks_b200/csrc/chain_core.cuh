@@ -57,15 +57,18 @@ struct ChainParams {  // read-only, shared by all chains of a run
   int P, max_par, W, Ws, n_samples;  // W = words per bitset, Ws = row stride of anc (odd when in smem)
   const double* C;      // centred Gram [P][ldc]
   int64_t ldc;
+  const double* diag;   // [P] its diagonal
+  ScoreConsts sc;       // N / 2 and the (N - 1) / (N - k - 1) table of the score
   const uint8_t* node_type;  // [P] 0 neither / 1 source / 2 sink
   const uint8_t* sim_edge;   // [parent + child*P] prior adjacency, src/network.h:138-146
   int n_sim_edges;
   double phi, omega;
   int initial_network, drop, n_iter, output_every;
   int trace_capacity, moves_capacity;
-  // prior graph (InitialNetwork == 0 start), [P][max_par] + [P]
+  // prior graph (InitialNetwork == 0 start), [P][prior_stride] + [P]
   const int* prior_par;
   const int* prior_npar;
+  int prior_stride;
   // row geometry of the ancestor bitsets for this warp width (set_row_geom)
   int g_chunks, g_lpr, g_rpp;
 };
@@ -75,6 +78,8 @@ struct ChainMem {  // per-chain global memory
   int* npar;           // [P]
   int* born;           // [P][max_par] first counted iteration of the edge (tabulation)
   double* base;        // [P] score of each node under the current graph
+  double* fac;         // [P][fac_stride(fac_mp(max_par))] Cholesky factor of each node's parent set (score_core.cuh)
+  double* rowbuf;      // [REPLAY_POS][row_stride(fac_mp(max_par))] candidate factor rows of the addition records
   uint32_t* anc;       // [P][Ws] ancestor bitsets
   uint32_t* haspar;    // [W] nodes with >= 1 parent (bitset)
   int* hp_list;        // [P] the same set as an ascending list (CurrOutputs, src/network.h:311-316)
@@ -94,11 +99,16 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int64_t iter;        // next iteration index
   int64_t read_pos;    // committed uniform stream position
   int valid;           // stale `valid` flag, src/bayesnet_mcmc.cpp:40
-  int te_m, fp_m, fn_m;  // members left by the last LogPrior(), src/network.h:262-275
+  int te_m;            // member TotalEdges as left by the last LogPrior(), src/network.h:262-267
   int te_true, agree_true, n_haspar;
+  // statistics: warp-uniform parts (sequential path) + lane-private parts (rounds: lane q adds
+  // what the iteration in its slot contributes; summed over the lanes when the chain ends)
   int proposed[3], reject[3];
   int n_rows, n_moves, n_nonpd;
   int64_t valid_iters;
+  int lane_prop[3], lane_rej[3], lane_nonpd, lane_valid;
+  int64_t lane_bytes;
+  int acc_add, acc_del;  // accepted moves since `drop`: the additions / deletions columns (src/network.h:340-341)
   int gll_ok; double gll;
   int64_t alg_bytes;   // sum over scored proposals of 8*(k'+1)(k'+2)/2 + 8
   long long cyc[6];    // cycles per phase: refill, replay (A), score (B/C), commit, accepted add, accepted delete
@@ -107,7 +117,7 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int windows;
   int need_full;       // the last round could not start: top the ring up completely before retrying
   int anc_changed;     // the last accepted move changed ancestor rows (else no cycle bit can differ)
-  int64_t next_log;    // a multiple of output_every that no logged iteration before s.iter precedes
+  int next_log;        // smallest multiple of output_every >= s.iter (rounds; n_iter is an int)
   int status;
 };
 
@@ -128,8 +138,11 @@ struct WindowSlots {  // shared memory on the device
   int s_k[WIN];     // walk result: record index of slot n (relative to the round start)
 };
 
+// Per-phase SM cycle counters (bn_chain_stats.phase_cycles) are a diagnostics build
+// (-DBN_PHASE_CYCLES, BN_B200_DIAG=1 of build.py): reading the clock a dozen times per epoch costs
+// the chain's warp a few percent, so the product build folds them to zero.
 BN_HD long long cycle_now() {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(BN_PHASE_CYCLES)
   return clock64();
 #else
   return 0;
@@ -640,15 +653,70 @@ BN_HD void anc_build_all(const ChainParams& p, ChainMem& m) {
   Warp::sync();
 }
 
+// Kernels with MaxPar > 8 keep a Cholesky factor per node (score_core.cuh): (re)factorise node c
+// for its current parent list; returns its score.
+template <int KMAX>
+BN_HD double factor_current(const ChainParams& p, const ChainMem& m, int c) {
+  const int MP = p.max_par, k = m.npar[c];
+  double* F = m.fac + (int64_t)c * fac_stride(fac_mp(MP));
+  if (k <= 8) {
+    Parents8 S;
+    const Par8 q = load_par8(p, m, c);
+#pragma unroll
+    for (int e = 0; e < 8; e++) S.s[e] = q.q[e];
+    return factor_node8(p.C, p.ldc, c, S, k, p.sc, F, fac_mp(MP));
+  }
+  return factor_node(p.C, p.ldc, c, m.par + (int64_t)c * MP, k, p.sc, F, fac_mp(MP));
+}
+
 // ---------------------------------------------------------------------------
 // Chain start: network::network graph part, src/network.h:115-122,138-170
 // ---------------------------------------------------------------------------
+// InitialNetwork == 1 (random start).  The reference's version (src/network.h:148-163) writes
+// edges[p][s] into vectors sized by the prior graph (out of bounds) and neither avoids duplicate
+// parents nor cycles, so it is undefined there; this is the defined variant with the same draw
+// order from the chain's uniform stream, before iteration 0: for every node that is not a source,
+// Npar = int(MaxPar * u) parents are drawn as int(P * u), re-drawn while the candidate is the node
+// itself, a sink, already a parent or an ancestor-closing choice (would create a cycle); a slot
+// that finds no parent in 100 draws (the reference's "> 100 tries" remark, :288,298) ends the
+// node's list.  Returns the number of uniforms consumed.
 template <int KMAX>
-BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
+BN_HD int64_t random_start(const ChainParams& p, ChainMem& m, RngStream& rng) {
+  const int P = p.P, MP = p.max_par;
+  int64_t pos = 0;
+  int anc_changed = 0;
+  for (int c = 0; c < P; c++) {
+    if (p.node_type[c] == 1) continue;
+    if (pos >= rng.gen_hi) rng_top_up(rng, pos);
+    const int want = (int)(MP * rng.ubuf[pos & (RNG_CAP - 1)]);
+    pos++;
+    for (int slot = 0; slot < want; slot++) {
+      int found = -1;
+      for (int tries = 0; tries < 100 && found < 0; tries++) {
+        if (pos >= rng.gen_hi) rng_top_up(rng, pos);
+        const int j = (int)(P * rng.ubuf[pos & (RNG_CAP - 1)]);
+        pos++;
+        int ok = (j != c && p.node_type[j] != 2 && !test_bit(m.anc + (int64_t)j * p.Ws, c));
+        for (int e = 0; e < slot; e++) if (m.par[(int64_t)c * MP + e] == j) ok = 0;
+        if (ok) found = j;
+      }
+      if (found < 0) break;
+      Warp::sync();
+      if (Warp::lane() == 0) { m.par[(int64_t)c * MP + slot] = found; m.npar[c] = slot + 1; }
+      Warp::sync();
+      anc_after_add(p, m, found, c, anc_changed);
+    }
+  }
+  return pos;
+}
+
+template <int KMAX>
+BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng) {
   const int l = Warp::lane(), P = p.P, MP = p.max_par;
   for (int64_t i = l; i < (int64_t)P * MP; i += Warp::NL) {
     // unused slots hold -1 (load_par8 relies on it)
-    m.par[i] = (p.initial_network == 0 && (int)(i % MP) < p.prior_npar[i / MP]) ? p.prior_par[i] : -1;
+    const int c = (int)(i / MP), e = (int)(i % MP);
+    m.par[i] = (p.initial_network == 0 && e < p.prior_npar[c]) ? p.prior_par[(int64_t)c * p.prior_stride + e] : -1;
     m.born[i] = p.drop;  // edges of the start graph are counted from iteration `drop`
   }
   if (m.npar_freq)
@@ -656,6 +724,11 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   for (int i = l; i < P; i += Warp::NL) m.npar[i] = (p.initial_network == 0) ? p.prior_npar[i] : 0;
   for (int w = l; w < p.W; w += Warp::NL) m.haspar[w] = 0u;
   Warp::sync();
+  int64_t start_pos = 0;
+  if (p.initial_network == 1) {
+    anc_reset(p, m);
+    start_pos = random_start<KMAX>(p, m, rng);
+  }
   if (l == 0) {
     int te = 0, ag = 0, nh = 0;
     for (int c = 0; c < P; c++) {
@@ -672,31 +745,28 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s) {
   s.agree_true = Warp::shfl(s.agree_true, 0);
   s.n_haspar = Warp::shfl(s.n_haspar, 0);
   Warp::sync();
-  if (s.te_true > 0) anc_build_all(p, m);
+  if (p.initial_network == 1) { /* ancestor rows were kept while the graph was drawn */ }
+  else if (s.te_true > 0) anc_build_all(p, m);
   else anc_reset(p, m);
-  // base scores
+  // base scores (and the per-node factors of the MaxPar > 8 kernels)
   s.n_nonpd = 0;
   for (int c = l; c < P; c += Warp::NL) {
-    const int k = m.npar[c];
-    int npd = 0;
-    // the score does not depend on MaxPar: sets of up to 8 parents take the register-resident
-    // scorer whatever the limit is (MaxPar = 50 is the R default; real parent sets are small)
-    if (KMAX <= 8 || k <= 8) {
+    if (KMAX <= 8) {
       Parents8 S;
+      const int k = m.npar[c];
 #pragma unroll
       for (int e = 0; e < 8; e++) S.s[e] = (e < k) ? m.par[(int64_t)c * MP + e] : c;
       m.base[c] = score_set8(p.C, p.ldc, c, S, k, p.n_samples);
-      npd = (m.base[c] == -INFINITY) ? 1 : 0;
-    } else if constexpr (KMAX > 8) {
-      int kk = 0;
-      m.base[c] = score_set_big<KMAX>(p.C, p.ldc, c, m.par + (int64_t)c * MP, k, 0, 0, 0, p.n_samples, &kk, &npd);
+    } else {
+      m.base[c] = factor_current<KMAX>(p, m, c);
     }
   }
   Warp::sync();
-  s.iter = 0; s.read_pos = 0;
+  s.iter = 0; s.read_pos = start_pos;
   s.valid = 1;                       // src/bayesnet_mcmc.cpp:40
-  s.te_m = 0; s.fp_m = 0; s.fn_m = 0;  // members start at 0 (src/network.h:49-51,64)
-  for (int t = 0; t < 3; t++) { s.proposed[t] = 0; s.reject[t] = 0; }
+  s.te_m = 0;  // members start at 0 (src/network.h:49-51,64)
+  for (int t = 0; t < 3; t++) { s.proposed[t] = 0; s.reject[t] = 0; s.lane_prop[t] = 0; s.lane_rej[t] = 0; }
+  s.lane_nonpd = 0; s.lane_valid = 0; s.lane_bytes = 0; s.acc_add = 0; s.acc_del = 0;
   s.n_rows = 0; s.n_moves = 0; s.valid_iters = 0; s.alg_bytes = 0;
   s.gll_ok = 0; s.gll = 0.0;
   s.win = 4; s.windows = 0; s.status = 0; s.need_full = 0; s.anc_changed = 0; s.next_log = 0;
@@ -717,16 +787,21 @@ BN_HD double sum_base(const ChainParams& p, const ChainMem& m) {
 // Returns the number of slots filled; sets *overflow when a single iteration
 // outran the ring.
 // ---------------------------------------------------------------------------
+// `unbounded` (want == 1): the iteration is not speculative, so when it outruns the ring the ring
+// slides forward with it (the reference's rejection loops, src/network.h:283-299, have no limit);
+// *overflow = 2 when no legal child / parent exists at all (the reference would spin forever),
+// 3 when a replayed stream ran out inside a rejection loop.
 BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s,
-                  const RngStream& rng, WindowSlots& ws, int want, int* overflow) {
+                  RngStream& rng, WindowSlots& ws, int want, int* overflow, int unbounded = 0) {
   const int P = p.P, MP = p.max_par;
   int64_t pos = s.read_pos;
   int valid = s.valid, te_m = s.te_m;
-  const int64_t hi = rng.gen_hi;
+  int64_t hi = rng.gen_hi;
   int n = 0;
   *overflow = 0;
 #define BN_U(dst)                                        \
   do {                                                   \
+    if (pos >= hi && unbounded) { rng_top_up(rng, pos); hi = rng.gen_hi; } \
     if (pos >= hi) { ovf = 1; dst = 0.75; }              \
     else dst = rng.ubuf[pos & (RNG_CAP - 1)];            \
     pos++;                                               \
@@ -738,13 +813,28 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
     int type, c = 0, j = 0, e = -1;
     if (u > 0.5 || te_m < 3) {
       // propose_addition, src/network.h:281-306
+      if (unbounded) {
+        int any = 0;
+        for (int q = Warp::lane(); q < P; q += Warp::NL) any |= (p.node_type[q] != 1 && m.npar[q] < MP) ? 1 : 0;
+        if (Warp::ballot(any) == 0u) { *overflow = 2; return 0; }
+      }
       for (;;) {
         BN_U(u);
         c = (int)(P * u);
         if (ovf || (p.node_type[c] != 1 && m.npar[c] < MP)) break;
+        if (unbounded && rng.kind == RNG_REPLAY && pos > rng.replay_len) { *overflow = 3; return 0; }
       }
       const int kc = ovf ? 0 : m.npar[c];
       const int* pc = m.par + (int64_t)c * MP;
+      if (unbounded) {
+        int any = 0;
+        for (int q = Warp::lane(); q < P; q += Warp::NL) {
+          int ok = (p.node_type[q] != 2 && q != c);
+          for (int t = 0; t < kc; t++) if (pc[t] == q) ok = 0;
+          any |= ok;
+        }
+        if (Warp::ballot(any) == 0u) { *overflow = 2; return 0; }
+      }
       for (;;) {
         BN_U(u);
         j = (int)(P * u);
@@ -752,6 +842,7 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
         int ok = (p.node_type[j] != 2 && j != c);
         for (int q = 0; q < kc; q++) if (pc[q] == j) ok = 0;
         if (ok) break;
+        if (unbounded && rng.kind == RNG_REPLAY && pos > rng.replay_len) { *overflow = 3; return 0; }
       }
       type = 1;
       te_m = s.te_true;  // OldLogPrior = LogPrior(), :302
@@ -800,31 +891,44 @@ BN_HD int phase_a(const ChainParams& p, const ChainMem& m, const ChainScalars& s
 // ---------------------------------------------------------------------------
 template <int KMAX>
 BN_HD double score_proposal(const ChainParams& p, const ChainMem& m, int type, int c, int j, int del,
-                            int* kk_out, int* npd) {
-  const int* pc = m.par + (int64_t)c * p.max_par;
+                            double* rowout, int* kk_out, int* npd) {
+  const int MP = p.max_par;
+  const int* pc = m.par + (int64_t)c * MP;
   const int k = m.npar[c];
-  int kk = 0;
-  double nw = 0.0;
-  if (KMAX <= 8 || k + (type == 1 ? 1 : -1) <= 8) {  // (chain_init: small sets use the K = 8 scorer)
+  *kk_out = k + (type == 1 ? 1 : -1);
+  *npd = 0;
+  double nw;
+  if (KMAX <= 8) {
+    // MaxPar <= 8: register-resident Cholesky of the proposed set (push_back / erase order)
     Parents8 S;
     if (type == 1) {
-      kk = k + 1;
 #pragma unroll
       for (int e = 0; e < 8; e++) S.s[e] = (e < k) ? pc[e] : j;
     } else {
-      kk = k - 1;
 #pragma unroll
       for (int e = 0; e < 8; e++) {
         const int src = e + (e >= del ? 1 : 0);
         S.s[e] = (src < k) ? pc[src] : c;
       }
     }
-    nw = score_set8(p.C, p.ldc, c, S, kk, p.n_samples);
+    nw = score_set8(p.C, p.ldc, c, S, *kk_out, p.n_samples);
     *npd = (nw == -INFINITY) ? 1 : 0;
-  } else if constexpr (KMAX > 8) {
-    nw = score_set_big<KMAX>(p.C, p.ldc, c, pc, k, type, j, del, p.n_samples, &kk, npd);
+    return nw;
   }
-  *kk_out = kk;
+  // MaxPar > 8: O(k^2) on the node's cached factor
+  const double* F = m.fac + (int64_t)c * fac_stride(fac_mp(MP));
+  int flags = 0;
+  if (k <= 8) {
+    Parents8 S;
+    const Par8 q = load_par8(p, m, c);
+#pragma unroll
+    for (int e = 0; e < 8; e++) S.s[e] = q.q[e];
+    nw = score_move8(p.C, p.ldc, p.diag, c, S, k, type, j, del, p.sc, F, fac_mp(MP), rowout, &flags);
+  } else {
+    nw = score_move_stream<KMAX>(p.C, p.ldc, p.diag, c, pc, k, type, j, del, p.sc, F, fac_mp(MP), rowout, &flags);
+  }
+  if (flags == SCORE_NOFACTOR) nw = score_scratch<KMAX>(p.C, p.ldc, c, pc, k, del, p.n_samples, npd);
+  else if (flags == SCORE_NPD) *npd = 1;
   return nw;
 }
 
@@ -849,7 +953,7 @@ BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars&
     ws.fn_m[i] = p.n_sim_edges - ag_new;
   }
   int kk = 0, npd = 0;
-  const double nw = score_proposal<KMAX>(p, m, ws.type[i], c, j, ws.pos[i], &kk, &npd);
+  const double nw = score_proposal<KMAX>(p, m, ws.type[i], c, j, ws.pos[i], nullptr, &kk, &npd);
   ws.new_score[i] = nw;
   ws.kk[i] = kk;
   ws.nonpd[i] = (signed char)npd;
@@ -1047,7 +1151,9 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
     kk = m.npar[ws.t_c[slot]] - 1;
     npd = (sc == -INFINITY) ? 1 : 0;
   } else {
-    sc = score_proposal<KMAX>(p, m, (rec & REC_TYPE) ? 2 : 1, ws.t_c[slot], ws.t_j[slot], ws.t_e[slot], &kk, &npd);
+    sc = score_proposal<KMAX>(p, m, (rec & REC_TYPE) ? 2 : 1, ws.t_c[slot], ws.t_j[slot], ws.t_e[slot],
+                              KMAX > 8 ? m.rowbuf + (uint32_t)slot * (uint32_t)row_stride(fac_mp(p.max_par)) : nullptr,
+                              &kk, &npd);
     if (cache) *cache = sc;  // (duplicates within a round store the same value)
   }
   ws.t_score[slot] = sc;
@@ -1234,12 +1340,28 @@ BN_HD void write_row(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t
   write_row_vals(p, m, s, it, ws.child[i], ws.type[i], ws.fn_m[i], ws.fp_m[i], additions, deletions);
 }
 
+// `newrow`: the candidate factor row of an accepted addition record (score_core.cuh), or null
+// (sequential path): the node is re-factorised instead.
+template <int KMAX>
 BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it, int type, int c,
-                           int j, int del, double new_score, int ag) {
+                           int j, int del, double new_score, int ag, const double* newrow) {
   const int MP = p.max_par, l = Warp::lane();
   int* pc = m.par + (int64_t)c * MP;
   int* bc = m.born + (int64_t)c * MP;
   const int k = m.npar[c];
+  double* F = KMAX > 8 ? m.fac + (int64_t)c * fac_stride(fac_mp(MP)) : nullptr;
+#if defined(__CUDA_ARCH__)
+  // (MaxPar > 8) the accepted record's candidate row (score_core.cuh) becomes row k of the factor: one 16-byte
+  // pair per lane; the loads are issued here and the stores follow the ancestor update (an L2
+  // round trip hidden)
+  D2 rv, rd, rr;
+  rv.x = rv.y = rd.x = rd.y = rr.x = rr.y = 0.0;
+  if (KMAX > 8 && type == 1 && newrow) {
+    if (2 * l < k) rv = ld2_l2(newrow + 2 * l);
+    rd = ld2_l2(newrow + row_tail(fac_mp(MP)));
+    rr = ld2_l2(newrow + row_tail(fac_mp(MP)) + 2);
+  }
+#endif
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
   Warp::sync();
   if (l == 0 && m.npar_freq) {
@@ -1254,6 +1376,7 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
       pc[k] = j; m.npar[c] = k + 1;
       if (m.edge_freq) bc[k] = (int)first_counted;  // birth iterations only feed the tabulation
       m.base[c] = new_score;
+      if (KMAX > 8 && !newrow) factor_current<KMAX>(p, m, c);
     }
     if (k == 0) {
       Warp::sync();
@@ -1275,7 +1398,8 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
         for (int e = del; e + 1 < k; e++) bc[e] = bc[e + 1];
       pc[k - 1] = -1;
       m.npar[c] = k - 1;
-      m.base[c] = new_score;
+      // (MaxPar > 8: later proposals at c are compared with the score of the new factor)
+      m.base[c] = KMAX > 8 ? factor_current<KMAX>(p, m, c) : new_score;
     }
     if (k == 1) {
       Warp::sync();
@@ -1286,6 +1410,23 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     s.te_true--; s.agree_true -= ag;
     Warp::sync();
     anc_after_delete(p, m, c, s.anc_changed);
+  }
+  if (KMAX > 8 && type == 1 && newrow) {
+    const int mp = fac_mp(MP);
+#if defined(__CUDA_ARCH__)
+    const double r = rsqrt_f64(rd.x);
+    if (2 * l <= k) {
+      if (2 * l == k) rv.x = r;
+      if (2 * l + 1 == k) rv.y = r;
+      *(D2*)(F + fac_row(k) + 2 * l) = rv;
+    }
+    if (l == 0) { F[fac_zoff(mp) + k] = rd.y * r; F[fac_tail(mp)] = rr.x; }
+#else
+    const double r = rsqrt_f64(newrow[row_tail(mp)]);
+    for (int t = 0; t < k; t++) F[fac_row(k) + t] = newrow[t];
+    F[fac_row(k) + k] = r;
+    F[fac_zoff(mp) + k] = newrow[row_tail(mp) + 1] * r; F[fac_tail(mp)] = newrow[row_tail(mp) + 2];
+#endif
   }
   if (m.dscore) {  // the deletion scores of c are no longer valid
     double* dc = m.dscore + (uint32_t)c * (uint32_t)MP;
@@ -1302,13 +1443,15 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
   Warp::sync();
 }
 
+template <int KMAX>
 BN_HD void apply_move(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it,
                       const WindowSlots& ws, int i) {
   const int ag = p.sim_edge[(int64_t)ws.parent[i] + (int64_t)ws.child[i] * p.P] ? 1 : 0;
-  apply_move_vals(p, m, s, it, ws.type[i], ws.child[i], ws.parent[i], ws.pos[i], ws.new_score[i], ag);
+  apply_move_vals<KMAX>(p, m, s, it, ws.type[i], ws.child[i], ws.parent[i], ws.pos[i], ws.new_score[i], ag, nullptr);
 }
 
 // Commit slots [0, ncommit): all but possibly the last are rejections/invalid.
+template <int KMAX>
 BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const WindowSlots& ws,
                   int ncommit) {
   // One lane per slot: the counters are ballots + popcounts instead of a sequential loop.
@@ -1340,9 +1483,8 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
       const int b = ffs32(lg) - 1;
       lg &= lg - 1;
       const uint32_t upto = (b == 31) ? 0xffffffffu : ((2u << b) - 1u);
-      write_row(p, m, s, s.iter + i0 + b, ws, i0 + b,
-                (s.proposed[1] + popc32(m_p1 & upto)) - (s.reject[1] + popc32(m_r1 & upto)),
-                (s.proposed[2] + popc32(m_p2 & upto)) - (s.reject[2] + popc32(m_r2 & upto)));
+      (void)upto;  // (only the last committed slot can be an acceptance)
+      write_row(p, m, s, s.iter + i0 + b, ws, i0 + b, s.acc_add, s.acc_del);
     }
     s.valid_iters += popc32(m_valid);
     s.alg_bytes += bytes;
@@ -1353,18 +1495,17 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
     if (m_acc) {
       const int b = ffs32(m_acc) - 1;  // == the last committed slot
       const long long ta = cycle_now();
-      apply_move(p, m, s, s.iter + i0 + b, ws, i0 + b);
+      apply_move<KMAX>(p, m, s, s.iter + i0 + b, ws, i0 + b);
       const long long dt = cycle_now() - ta;
       s.cyc[ws.type[i0 + b] == 1 ? 4 : 5] += dt;
       s.cyc[3] -= dt;
-      if (m_log & m_acc)
-        write_row(p, m, s, s.iter + i0 + b, ws, i0 + b, s.proposed[1] - s.reject[1],
-                  s.proposed[2] - s.reject[2]);
+      if (s.iter + i0 + b >= p.drop) { if (ws.type[i0 + b] == 1) s.acc_add++; else s.acc_del++; }
+      if (m_log & m_acc) write_row(p, m, s, s.iter + i0 + b, ws, i0 + b, s.acc_add, s.acc_del);
     }
   }
   const int last = ncommit - 1;
   s.valid = ws.valid[last];
-  s.te_m = ws.te_m[last]; s.fp_m = ws.fp_m[last]; s.fn_m = ws.fn_m[last];
+  s.te_m = ws.te_m[last];
   s.read_pos = ws.pos_after[last];
   s.iter += ncommit;
   // lanes are not in lockstep: nobody may still be reading the slots when lane 0
@@ -1377,6 +1518,7 @@ BN_HD void commit(const ChainParams& p, ChainMem& m, ChainScalars& s, const Wind
 // as commit(), with the slot of iteration s.iter + q living in the registers of lane q.
 // Returns the number of iterations committed; *accepted / *acc_c / *acc_type describe the
 // accepted move, *stop (WALK_OVF / WALK_STALE / WALK_END or 0) the record that ended the walk.
+template <int KMAX>
 BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const WindowSlots& ws, int64_t round_pos,
                       int* k_io, int want, int* stop, int* accepted, int* acc_c, int* acc_type) {
   const int l = Warp::lane();
@@ -1409,64 +1551,62 @@ BN_HD int round_epoch(const ChainParams& p, ChainMem& m, ChainScalars& s, const 
   const int last = n - 1;
   const bool in = l < n;
   const int rec = in ? ws.t_rec[myk] : 0;
-  const int child = in ? ws.t_c[myk] : 0;
   const int type = (rec & REC_TYPE) ? 2 : 1;
   const bool valid = in && myvalid;
-  const int it = (int)s.iter + l;  // n_iter is an int
+  const int it0 = (int)s.iter, it = it0 + l;  // n_iter is an int
   const bool counted = valid && it >= p.drop;  // src/network.h:331, src/bayesnet_mcmc.cpp:58
-  const uint32_t accbit = acc ? (1u << last) : 0u;  // only the last slot can be an acceptance
-  const uint32_t m_valid = Warp::ballot(valid);
-  const uint32_t m_inval = Warp::ballot(in && !valid);
-  const uint32_t m_p1 = Warp::ballot(counted && type == 1);
-  const uint32_t m_p2 = Warp::ballot(counted && type == 2);
-  const uint32_t m_r1 = m_p1 & ~accbit, m_r2 = m_p2 & ~accbit;
-  const uint32_t m_npd = Warp::ballot(valid && (rec & REC_NPD));
-  // logged iterations (i % output == 0, :63-65): at most one per epoch when output >= the epoch
-  // length, found by comparing with the next multiple instead of a division per lane
-  while (s.next_log < s.iter) s.next_log += p.output_every;  // warp-uniform, rarely more than one step
-  const bool logged = (p.output_every >= WIN) ? (it == (int)s.next_log) : (it % p.output_every == 0);
-  const uint32_t m_log = Warp::ballot(valid && logged);
-  const int kk = valid ? (rec >> REC_KK_SHIFT) : 0;
-  const int bytes = Warp::sum(valid ? 4 * (kk + 1) * (kk + 2) + 8 : 0);
-  // members left by the last LogPrior(): the proposed graph for valid iterations
-  // (checker(), src/network.h:333), the current graph otherwise
-  const int ag = (rec & REC_AG) ? 1 : 0;
-  const int te_m = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
-  const int ag_new = valid ? s.agree_true + (type == 1 ? ag : -ag) : s.agree_true;
-  const int fp_m = te_m - ag_new, fn_m = p.n_sim_edges - ag_new;
-  // rows of rejected iterations (pre-move graph), in order
-  uint32_t lg = m_log & ~accbit;
-  while (lg) {
-    const int b = ffs32(lg) - 1;
-    lg &= lg - 1;
-    const uint32_t upto = (b == 31) ? 0xffffffffu : ((2u << b) - 1u);
-    write_row_vals(p, m, s, s.iter + b, Warp::shfl(child, b), Warp::shfl(type, b), Warp::shfl(fn_m, b),
-                   Warp::shfl(fp_m, b),
-                   (s.proposed[1] + popc32(m_p1 & upto)) - (s.reject[1] + popc32(m_r1 & upto)),
-                   (s.proposed[2] + popc32(m_p2 & upto)) - (s.reject[2] + popc32(m_r2 & upto)));
+  const bool is_acc = acc && l == last;        // only the last slot can be an acceptance
+  // statistics stay lane-private (no ballots or reductions per epoch)
+  // (constant indices only: a run-time index would move the scalars to local memory)
+  s.lane_prop[1] += (counted && type == 1) ? 1 : 0;
+  s.lane_prop[2] += (counted && type == 2) ? 1 : 0;
+  s.lane_rej[1] += (counted && type == 1 && !is_acc) ? 1 : 0;
+  s.lane_rej[2] += (counted && type == 2 && !is_acc) ? 1 : 0;
+  s.lane_rej[0] += (in && !myvalid) ? 1 : 0;  // notValid(), src/network.h:434-437 (not guarded by drop)
+  if (valid) {
+    const int kk = rec >> REC_KK_SHIFT;
+    s.lane_valid++;
+    s.lane_bytes += 4 * (kk + 1) * (kk + 2) + 8;
+    if (rec & REC_NPD) s.lane_nonpd++;
   }
-  s.valid_iters += popc32(m_valid);
-  s.alg_bytes += bytes;
-  s.proposed[1] += popc32(m_p1); s.proposed[2] += popc32(m_p2);
-  s.reject[0] += popc32(m_inval);  // notValid(), src/network.h:434-437 (not guarded by drop)
-  s.reject[1] += popc32(m_r1); s.reject[2] += popc32(m_r2);
-  s.n_nonpd += popc32(m_npd);
-  const int te_last = Warp::shfl(te_m, last), fp_last = Warp::shfl(fp_m, last), fn_last = Warp::shfl(fn_m, last);
+  // logged iterations (i % output == 0, :63-65): s.next_log is the next multiple at or behind it0
+  int log_acc = 0, fn_acc = 0, fp_acc = 0;
+  if (s.next_log < it0 + n) {  // rare
+    // members left by the last LogPrior(): the proposed graph for valid iterations
+    // (checker(), src/network.h:333), the current graph otherwise
+    const int ag = (rec & REC_AG) ? 1 : 0;
+    const int te_m = valid ? s.te_true + (type == 1 ? 1 : -1) : s.te_true;
+    const int ag_new = valid ? s.agree_true + (type == 1 ? ag : -ag) : s.agree_true;
+    const int fp_m = te_m - ag_new, fn_m = p.n_sim_edges - ag_new;
+    const int child = in ? ws.t_c[myk] : 0;
+    do {
+      const int b = s.next_log - it0;
+      const int b_valid = Warp::shfl(valid ? 1 : 0, b), b_child = Warp::shfl(child, b), b_type = Warp::shfl(type, b);
+      const int b_fn = Warp::shfl(fn_m, b), b_fp = Warp::shfl(fp_m, b);
+      if (acc && b == last) { log_acc = 1; fn_acc = b_fn; fp_acc = b_fp; }  // its row sees the post-move graph
+      else if (b_valid) write_row_vals(p, m, s, it0 + b, b_child, b_type, b_fn, b_fp, s.acc_add, s.acc_del);
+      s.next_log += p.output_every;
+    } while (s.next_log < it0 + n);
+  }
+  const int info_last = Warp::shfl((valid ? 4 : 0) | type, last);
   long long dt = 0;
   if (acc) {
     const int c = ws.t_c[k_acc], a_type = (ws.t_rec[k_acc] & REC_TYPE) ? 2 : 1;
     const long long ta = cycle_now();
-    apply_move_vals(p, m, s, s.iter + last, a_type, c, ws.t_j[k_acc], ws.t_e[k_acc], ws.t_score[k_acc],
-                    (ws.t_rec[k_acc] & REC_AG) ? 1 : 0);
+    apply_move_vals<KMAX>(p, m, s, it0 + last, a_type, c, ws.t_j[k_acc], ws.t_e[k_acc], ws.t_score[k_acc],
+                          (ws.t_rec[k_acc] & REC_AG) ? 1 : 0,
+                          KMAX > 8 ? m.rowbuf + (uint32_t)k_acc * (uint32_t)row_stride(fac_mp(p.max_par)) : nullptr);
     dt = cycle_now() - ta;
     s.cyc[a_type == 1 ? 4 : 5] += dt;
-    if (m_log & accbit)
-      write_row_vals(p, m, s, s.iter + last, c, a_type, fn_last, fp_last, s.proposed[1] - s.reject[1],
-                     s.proposed[2] - s.reject[2]);
+    if (it0 + last >= p.drop) { if (a_type == 1) s.acc_add++; else s.acc_del++; }
+    if (log_acc) write_row_vals(p, m, s, it0 + last, c, a_type, fn_acc, fp_acc, s.acc_add, s.acc_del);
     *acc_c = c; *acc_type = a_type;
+    // (the move was applied: te_true already counts it)
+    s.te_m = s.te_true;
+  } else {
+    s.te_m = (info_last & 4) ? s.te_true + ((info_last & 3) == 1 ? 1 : -1) : s.te_true;
   }
   s.valid = v;
-  s.te_m = te_last; s.fp_m = fp_last; s.fn_m = fn_last;
   s.read_pos = round_pos + k;
   s.iter += n;
   // the caller charges the whole call to the walk: move the commit part and the move over
@@ -1484,6 +1624,7 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   RoundCtx rc;
   rc.pos = s.read_pos; rc.hi = rng.gen_hi;
   rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+  while (s.next_log < (int)s.iter) s.next_log += p.output_every;  // (after sequential windows; else no step)
   team_records<KMAX>(p, m, rc, rng.ubuf, ws);
   long long t1 = cycle_now();
   s.cyc[1] += t1 - t0;
@@ -1495,7 +1636,7 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     if (want <= 0) break;
     int stop = 0, accepted = 0, c = 0, type = 0;
     const int k0 = k, nh0 = s.n_haspar;
-    const int n = round_epoch(p, m, s, ws, rc.pos, &k, want, &stop, &accepted, &c, &type);
+    const int n = round_epoch<KMAX>(p, m, s, ws, rc.pos, &k, want, &stop, &accepted, &c, &type);
     s.cyc[2] += cycle_now() - t0;
     if (n == 0) {
       // one iteration needs more uniforms than a record can count: the sequential path takes it
@@ -1526,7 +1667,7 @@ template <int KMAX>
 BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
                      WindowSlots& ws) {
   const int l = Warp::lane();
-  chain_init<KMAX>(p, m, s);
+  chain_init<KMAX>(p, m, s, rng);
   for (int i = REPLAY_POS + l; i < 2 * REPLAY_POS; i += Warp::NL) ws.t_walk[i] = WALK_END;
   Warp::sync();
 #if defined(__CUDA_ARCH__)
@@ -1554,11 +1695,13 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     int want = s.need_full ? 1 : s.win;
     if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
     int overflow = 0;
-    const int n = phase_a(p, m, s, rng, ws, want, &overflow);
+    int n = phase_a(p, m, s, rng, ws, want, &overflow);
     if (n == 0) {
-      if (s.need_full) { s.status = 4; break; }  // BN_ERR_NO_LEGAL_PROPOSAL: one iteration outran the full ring
-      s.need_full = 1;
-      continue;
+      if (!s.need_full) { s.need_full = 1; continue; }  // top the ring up completely and retry
+      // one iteration needs more uniforms than the ring holds (legal nodes are rare): no limit
+      n = phase_a(p, m, s, rng, ws, 1, &overflow, 1);
+      // BN_ERR_NO_LEGAL_PROPOSAL: no legal node exists at all; BN_ERR_CAPACITY: the replay buffer ran out
+      if (n == 0) { s.status = (overflow == 3) ? 6 : 4; break; }
     }
     s.need_full = 0;
     t0 = cycle_now();
@@ -1575,7 +1718,7 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     t1 = cycle_now();
     s.cyc[2] += t1 - t0;
     const int ncommit = (first >= 0) ? first + 1 : n;
-    commit(p, m, s, ws, ncommit);
+    commit<KMAX>(p, m, s, ws, ncommit);
     s.cyc[3] += cycle_now() - t1;
     if (first >= 0) {
       int w = 2 * (first + 1);
@@ -1585,6 +1728,11 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
       s.win = w > WIN ? WIN : w;
     }
   }
+  // fold the lane-private statistics of the rounds into the warp-uniform totals
+  for (int t = 0; t < 3; t++) { s.proposed[t] += Warp::sum(s.lane_prop[t]); s.reject[t] += Warp::sum(s.lane_rej[t]); }
+  s.n_nonpd += Warp::sum(s.lane_nonpd);
+  s.valid_iters += Warp::sum(s.lane_valid);
+  s.alg_bytes += (int64_t)Warp::sum((long long)s.lane_bytes);
   // flush the posterior tabulation of the surviving edges / parent counts
   if (m.npar_freq) {
     Warp::sync();

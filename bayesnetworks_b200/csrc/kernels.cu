@@ -21,6 +21,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
   __shared__ double ubuf[RNG_CAP];
   __shared__ WindowSlots ws;
   __shared__ int helper_cmd[HELPER_WORDS];
+  __shared__ double dof_ratio[KMAX + 2];
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x;
@@ -57,18 +58,25 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
   m.npar_freq = w.npar_freq ? w.npar_freq + ch * P * (MP + 1) : nullptr;
   m.npar_since = w.npar_since ? w.npar_since + ch * P : nullptr;
   m.dscore = w.dscore ? w.dscore + ch * P * MP : nullptr;
+  m.fac = w.fac ? w.fac + ch * P * fac_stride(fac_mp(p.max_par)) : nullptr;   // (MaxPar > 8 only)
+  m.rowbuf = w.rowbuf ? w.rowbuf + (int64_t)ch * REPLAY_POS * row_stride(fac_mp(p.max_par)) : nullptr;
   m.helper = helper_cmd;
 
   RngStream rng;
   if (ra.kind == RNG_WH)
     rng_init_wh(rng, ra.seeds[3 * ch], ra.seeds[3 * ch + 1], ra.seeds[3 * ch + 2], ubuf);
   else if (ra.kind == RNG_RMT)
-    rng_init_rmt(rng, ra.mt_states + (int64_t)ch * 624, ubuf);
+    rng_init_rmt(rng, ra.mt_states + (int64_t)ch * 624, ra.mt_pos[ch], ubuf);
   else
     rng_init_replay(rng, ra.replay + (int64_t)ch * ra.replay_len, ra.replay_len, ubuf);
 
   ChainParams pp = p;
   set_row_geom(pp);
+  // (N - 1) / (N - k - 1), src/network.h:232-234 (int N, int Npar)
+  for (int k = threadIdx.x; k < KMAX + 2; k += blockDim.x)
+    dof_ratio[k] = (double)(p.n_samples - 1) / (double)(p.n_samples - k - 1);
+  pp.sc.half_n = (double)p.n_samples / 2.0;
+  pp.sc.ratio = dof_ratio;
   if (!m.moves) pp.moves_capacity = 0;
   if (ALL_SMEM || sm.off_types >= 0) {
     uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);
@@ -81,7 +89,9 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
     return;
   }
   ChainScalars s;
+  const long long clk0 = clock64();
   run_chain<KMAX>(pp, m, s, rng, ws);
+  const long long clk1 = clock64();
   if (lane == 0) helper_cmd[0] = HELPER_EXIT;
   __syncwarp();
   cta_bar(1);
@@ -106,6 +116,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
     r.n_moves = s.n_moves;
     for (int t = 0; t < 6; t++) r.cyc[t] = s.cyc[t];
     r.slots_sim = s.slots_sim;
+    r.cyc_total = clk1 - clk0;
   }
 }
 
@@ -162,8 +173,10 @@ static const char* launch_chains_t(ChainParams p, const ChainWorkspace& w, const
 const char* launch_chains(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
                           ChainResult* d_results, int n_chains, cudaStream_t stream) {
   if (p.max_par <= 8) return launch_chains_t<8>(p, w, ra, d_results, n_chains, stream);
+#if !defined(BN_DEV_BUILD_K8_ONLY)  // (developer switch of build.py: compile the MaxPar <= 8 kernels only)
   if (p.max_par <= 16) return launch_chains_t<16>(p, w, ra, d_results, n_chains, stream);
   if (p.max_par <= 64) return launch_chains_t<64>(p, w, ra, d_results, n_chains, stream);
+#endif
   return "max_par > 64 is not supported";
 }
 

@@ -16,6 +16,8 @@ struct ChainWorkspace {  // arrays over all chains of a run (device memory)
   int* t_add; int* t_del; int* t_fn; int* t_fp;
   int* moves; int* edge_freq; int* npar_freq; int* npar_since;
   double* dscore;                      // [nc][P][max_par] deletion-score cache (all-ones = unknown)
+  double* fac;                         // [nc][P][fac_stride(max_par)] per-node Cholesky factors
+  double* rowbuf;                      // [nc][REPLAY_POS][row_stride(max_par)] candidate rows of a round
 };
 
 // Which per-chain arrays live in dynamic shared memory (byte offset, -1 = global memory).
@@ -33,6 +35,7 @@ struct ChainRngArgs {
   int kind;
   const int* seeds;          // [3*n_chains]
   uint32_t* mt_states;       // [624*n_chains] (R-MT)
+  const int* mt_pos;         // [n_chains] position within the state (624 = regenerate first)
   const double* replay;      // [replay_len*n_chains]
   int64_t replay_len;
 };
@@ -41,7 +44,7 @@ struct ChainResult {
   int64_t uniforms, valid_iters, alg_bytes;
   int proposed[3], reject[3];
   int n_nonpd, total_edges, status, windows, n_rows, n_moves;
-  long long cyc[6], slots_sim;
+  long long cyc[6], slots_sim, cyc_total;
 };
 
 struct SweepParams {

@@ -57,9 +57,9 @@ BN_HD void rng_init_wh(RngStream& r, int ix, int iy, int iz, double* ubuf) {
   r.mt = nullptr; r.mti = 0; r.replay = nullptr; r.replay_len = 0;
 }
 
-BN_HD void rng_init_rmt(RngStream& r, uint32_t* mt_state, double* ubuf) {
+BN_HD void rng_init_rmt(RngStream& r, uint32_t* mt_state, int mti, double* ubuf) {
   r.kind = RNG_RMT;
-  r.mt = mt_state; r.mti = 624;  // set.seed() leaves the position at 624 = regenerate
+  r.mt = mt_state; r.mti = mti;  // set.seed() leaves the position at 624 = regenerate
   r.ubuf = ubuf; r.gen_hi = 0;
   r.x = r.y = r.z = r.mx = r.my = r.mz = 0; r.replay = nullptr; r.replay_len = 0;
 }

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BN_B200_ABI_VERSION 2
+#define BN_B200_ABI_VERSION 3
 
 /* ---- status codes -------------------------------------------------------- */
 enum {
@@ -30,20 +30,22 @@ enum {
   BN_ERR_BAD_ARG = 1,            /* NULL pointer, size <= 0, edge index out of range, ... */
   BN_ERR_CUDA = 2,               /* a CUDA runtime/driver call failed */
   BN_ERR_OOM = 3,                /* device or host allocation failed */
-  BN_ERR_NO_LEGAL_PROPOSAL = 4,  /* a single iteration needed more uniforms than the stream
-                                    window holds: no legal node exists (the reference would
-                                    spin forever in src/network.h:283-299) */
+  BN_ERR_NO_LEGAL_PROPOSAL = 4,  /* no legal child / parent exists at all (every candidate child is
+                                    a source or at max_par, every candidate parent a sink or
+                                    already a parent): the reference would spin forever in
+                                    src/network.h:283-299.  Rare-but-legal proposals never fail:
+                                    an iteration may consume any number of uniforms */
   BN_ERR_NO_DEVICE = 5,          /* no CUDA device / device index out of range */
   BN_ERR_CAPACITY = 6,           /* caller buffer too small */
-  BN_ERR_UNSUPPORTED = 7         /* e.g. InitialNetwork == 1 (undefined behaviour in the
-                                    reference, src/network.h:151-157) */
+  BN_ERR_UNSUPPORTED = 7         /* e.g. max_par > 64 */
 };
 
 /* ---- uniform streams (replaces R::runif, call sites src/bayesnet_mcmc.cpp:48,
  *      src/network.h:284,292,309,318,319,335) ------------------------------ */
 enum {
   BN_RNG_WH = 0,      /* Wichmann-Hill, Bayes-networks/random4f.h:17-49; 3 seeds per chain */
-  BN_RNG_RMT = 1,     /* R's Mersenne-Twister incl. set.seed() scrambling; seeds[3c] = seed */
+  BN_RNG_RMT = 1,     /* R's Mersenne-Twister: set.seed(seeds[3c]) scrambling, or the stream state
+                         itself (bn_run_args.mt_state_in = .Random.seed[2:626]) */
   BN_RNG_REPLAY = 2   /* caller-supplied uniforms (replay_len per chain) */
 };
 
@@ -59,7 +61,10 @@ int bn_device_count(void);
  * the prior adjacency simEdge / NsimEdges (:138-146) and node types are
  * uploaded once.  X is column-major n_samples x n_nodes (R layout, X(n,p) =
  * X[n + p*n_samples]).  Edges are 1-based (source -> target), as in
- * graph$source / graph$target.  node_type: 0 neither, 1 source, 2 sink. */
+ * graph$source / graph$target.  node_type: 0 neither, 1 source, 2 sink.
+ * A node of the supplied graph may have more than max_par parents: with
+ * InitialNetwork = 2 the graph only feeds simEdge / NsimEdges (:138-146,164-169);
+ * bn_run refuses InitialNetwork = 0 in that case. */
 int bn_create(const double* X_colmajor, int n_samples, int n_nodes,
               const int* edge_src_1b, const int* edge_tgt_1b, int n_edges,
               const int* node_type, int max_par, double phi, double omega,
@@ -188,6 +193,8 @@ typedef struct bn_chain_stats {
                               (draw replay + scoring), walk + repair, commit, accepted additions,
                               accepted deletions */
   int64_t slots_simulated; /* iterations emitted by the record walk */
+  int64_t kernel_cycles;   /* SM cycles of the chain from its first to its last iteration (ABI >= 3);
+                              phase_cycles are filled by diagnostics builds only (-DBN_PHASE_CYCLES) */
 } bn_chain_stats;
 
 typedef struct bn_run_args {
@@ -198,7 +205,11 @@ typedef struct bn_run_args {
                               derived triple */
   const double* replay;    /* BN_RNG_REPLAY: [n_chains*replay_len] */
   int64_t replay_len;
-  int initial_network;     /* 0 = start from the prior graph, 2 = empty graph */
+  int initial_network;     /* 2 = empty graph; 1 = random graph drawn from the chain's own stream before
+                              iteration 0 (the defined variant of src/network.h:148-163, which is
+                              undefined behaviour in the reference: same draw order, but duplicate
+                              parents and cycle-closing parents are re-drawn, at most 100 draws per
+                              slot); any other value = start from the supplied graph (:148-170) */
   int drop;
   int n_iter;
   int output_every;
@@ -215,6 +226,15 @@ typedef struct bn_run_args {
   /* freqNpar of the same Tabulate(), main.cpp:291 (optional, may be NULL; ABI version >= 2):
      npar_freq[chain][node*(max_par+1) + k] = counted iterations the node spent with k parents */
   int* npar_freq;
+  /* R's Mersenne-Twister stream state (ABI >= 3; BN_RNG_RMT only; HOST memory whatever
+     device_outputs says; may be NULL).  625 ints per chain in the layout of R's
+     .Random.seed[2:626]: the position (dummy[0], 624 = regenerate first) and the 624 state
+     words.  mt_state_in: the chains start from this state instead of set.seed(seeds[3c]);
+     mt_state_out: the state after exactly the uniforms the chain consumed, i.e. what
+     GetRNGstate / R::runif x n / PutRNGstate of the reference leaves behind
+     (src/RcppExports.cpp:13, src/bayesnet_mcmc.cpp:48, src/network.h:284,292,309,318,319,335). */
+  const int* mt_state_in;
+  int* mt_state_out;
 } bn_run_args;
 
 /* final_parents: [n_chains][P][max_par] (-1 padded), final_n_par: [n_chains][P]; may be NULL.
@@ -230,14 +250,18 @@ int bn_run(bn_ctx* ctx, const bn_run_args* args, bn_trace* trace, int* final_par
  * One chain, one device (device 0).  graph_node_labels is accepted and unused, as
  * in the reference (src/bayesnet_mcmc.cpp:30).  The eight result columns are
  * written to caller arrays of `capacity` rows; returns the number of rows
- * (>= 0) or -(status) on error.  rng_kind/seeds select the uniform stream. */
+ * (>= 0) or -(status) on error.  rng_kind/seeds select the uniform stream; with
+ * BN_RNG_RMT, mt_state_in / mt_state_out carry R's stream state in and out (see
+ * bn_run_args), which is how the Rcpp glue keeps R's `bn_mcmc` after `set.seed` on the
+ * reference's trajectory and R's .Random.seed advanced as the reference leaves it. */
 int bn_main_fun(const double* X_colmajor, int n_samples, int n_nodes,
                 const int* graph_source, const int* graph_target, int n_edges,
                 const int* graph_node_labels, const int* graph_node_type,
                 int MaxPar, double phi, double omega, int InitialNetwork, int drop, int N,
                 int output, int rng_kind, const int* seeds,
                 int capacity, int* iter, int* ChangedNode, int* movetype, double* globalLL,
-                int* additions, int* deletions, int* FN, int* FP);
+                int* additions, int* deletions, int* FN, int* FP,
+                const int* mt_state_in /* [625] or NULL */, int* mt_state_out /* [625] or NULL */);
 
 #ifdef __cplusplus
 }

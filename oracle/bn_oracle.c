@@ -109,6 +109,10 @@ double bno_rng_uniform(bno_rng* r) {
   return u;
 }
 
+void bno_rng_skip(bno_rng* r, long n) {
+  for (long i = 0; i < n; i++) (void)bno_rng_uniform(r);
+}
+
 double bno_rng_uniform_cb(void* r) { return bno_rng_uniform((bno_rng*)r); }
 
 /* ========================================================================= */
@@ -339,31 +343,57 @@ int bno_mcmc(const bno_mcmc_args* a, bno_rng* rng, bno_trace* trace,
   memset(&ch, 0, sizeof(ch));
   ch.a = a; ch.N = a->N; ch.P = a->P; ch.max_par = a->max_par;
   int P = a->P, MP = a->max_par;
-  if (a->initial_network == 1) return -1; /* out-of-bounds writes in the reference (src/network.h:151-157) */
+  /* InitialNetwork: 1 = random start, 2 = empty graph, anything else keeps the supplied graph
+   * (src/network.h:148-170) */
+  const int init = (a->initial_network == 1 || a->initial_network == 2) ? a->initial_network : 0;
 
   ch.sumX = (double*)malloc(sizeof(double) * (size_t)P);
   ch.sumXX = (double*)malloc(sizeof(double) * (size_t)P * P);
   if (a->legacy) gram_legacy(a->X_colmajor, a->N, P, ch.sumX, ch.sumXX);
   else bno_gram(a->X_colmajor, a->N, P, ch.sumX, ch.sumXX);
 
-  /* src/network.h:115-122: parent lists from the 1-based edge list. */
+  /* src/network.h:115-122: parent lists from the 1-based edge list (edges[tgt-1].push_back(src-1));
+   * src/network.h:138-146: prior adjacency simEdge(parent, child) = 1, NsimEdges counts list entries.
+   * The supplied graph may exceed MaxPar parents per node as long as the chain does not start
+   * from it (with InitialNetwork == 2 it only feeds simEdge / NsimEdges, :164-169). */
   ch.par = (int*)malloc(sizeof(int) * (size_t)P * MP);
   ch.npar = (int*)calloc((size_t)P, sizeof(int));
   for (long i = 0; i < (long)P * MP; i++) ch.par[i] = -1;
+  ch.sim_edge = (unsigned char*)calloc((size_t)P * P, 1);
   for (int e = 0; e < a->n_edges; e++) {
     int child = a->edge_tgt_1b[e] - 1, parent = a->edge_src_1b[e] - 1;
-    if (ch.npar[child] >= MP) return -2;
-    ch.par[(size_t)child * MP + ch.npar[child]++] = parent;
-  }
-  /* src/network.h:138-146: prior adjacency. */
-  ch.sim_edge = (unsigned char*)calloc((size_t)P * P, 1);
-  for (int p = 0; p < P; p++)
-    for (int e = 0; e < ch.npar[p]; e++) {
-      ch.sim_edge[(size_t)ch.par[(size_t)p * MP + e] + (size_t)p * P] = 1;
-      ch.n_sim_edges++;
+    ch.sim_edge[(size_t)parent + (size_t)child * P] = 1;
+    ch.n_sim_edges++;
+    if (init == 0) {
+      if (ch.npar[child] >= MP) return -2;
+      ch.par[(size_t)child * MP + ch.npar[child]++] = parent;
     }
-  /* src/network.h:164-169: InitialNetwork == 2 starts from the empty graph. */
-  if (a->initial_network == 2) memset(ch.npar, 0, sizeof(int) * (size_t)P);
+  }
+  if (init == 1) {
+    /* Random start.  The reference's own version (src/network.h:148-163) writes edges[p][s] into
+     * vectors sized by the prior graph (out of bounds) and avoids neither duplicate parents nor
+     * cycles: undefined behaviour, NOT a parity target.  This is the defined variant the CUDA path
+     * implements (include/bn_b200.h): same draw order from the chain's stream before iteration 0
+     * -- for every non-source node Npar = int(MaxPar * u), then each parent as int(P * u) -- but a
+     * candidate that is the node itself, a sink, already a parent or cycle-closing is re-drawn,
+     * and a slot that finds no parent in 100 draws ends the node's list. */
+    for (int p = 0; p < P; p++) {
+      if (a->node_type[p] == 1) continue;
+      int want = (int)(MP * bno_rng_uniform(rng));
+      for (int s = 0; s < want; s++) {
+        int found = -1;
+        for (int tries = 0; tries < 100 && found < 0; tries++) {
+          int src = (int)(P * bno_rng_uniform(rng));
+          int ok = (src != p && a->node_type[src] != 2 && !chain_path_exists(&ch, src, p));
+          for (int e = 0; e < s; e++) if (ch.par[(size_t)p * MP + e] == src) ok = 0;
+          if (ok) found = src;
+        }
+        if (found < 0) break;
+        ch.par[(size_t)p * MP + s] = found;
+        ch.npar[p] = s + 1;
+      }
+    }
+  }
 
   int proposed[3] = {0, 0, 0}, reject[3] = {0, 0, 0};
   int valid = 1;  /* src/bayesnet_mcmc.cpp:40 */

@@ -48,6 +48,7 @@ void bno_rng_init_rmt(bno_rng* r, uint32_t seed);          /* == set.seed(seed) 
 void bno_rng_init_replay(bno_rng* r, const double* u, long n);
 double bno_rng_uniform(bno_rng* r);                          /* == R::runif(0,1) / RandomUniform() */
 double bno_rng_uniform_cb(void* r);                          /* void* adaptor */
+void bno_rng_skip(bno_rng* r, long n);                       /* draw and discard n uniforms */
 
 /* ---- dense linear algebra (src/cholesky22.h) ---------------------------- */
 int bno_cholesky_decomp(const double* x, int n, double* c);  /* :25-66, row-major n*n */

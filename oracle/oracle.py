@@ -150,6 +150,21 @@ class Oracle:
             self.lib.bno_rng_init_replay(C.byref(r), _d(replay), C.c_long(len(replay)))
         return r
 
+    def rmt_state_after(self, seed, n_draws, state=None):
+        """R's Mersenne-Twister state as .Random.seed[2:626] (position + 624 words, int32) after
+        ``set.seed(seed)`` -- or starting from ``state`` (625 ints) -- and ``n_draws`` uniforms."""
+        r = self._rng(RNG_RMT, (seed,) if state is None else (0,))
+        if state is not None:
+            st = (np.asarray(state).astype(np.int64) & 0xFFFFFFFF).astype(np.uint32)
+            r.mti = int(st[0])
+            for i in range(624):
+                r.mt[i] = int(st[1 + i])
+        self.lib.bno_rng_skip(C.byref(r), C.c_long(int(n_draws)))
+        out = np.empty(625, dtype=np.uint32)
+        out[0] = r.mti
+        out[1:] = np.frombuffer(r.mt, dtype=np.uint32)
+        return out.view(np.int32)
+
     def uniforms(self, n, kind=RNG_WH, seeds=None):
         r = self._rng(kind, seeds)
         return np.array([self.lib.bno_rng_uniform(C.byref(r)) for _ in range(n)])

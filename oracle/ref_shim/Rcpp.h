@@ -24,6 +24,7 @@
 #include <initializer_list>
 #include <utility>
 #include <stdexcept>
+#include <map>
 
 namespace Rcpp {
 
@@ -116,6 +117,20 @@ struct ShimErrStream {
 };
 extern ShimErrStream Rcerr;
 
+// R's global environment, as far as the B200 glue (bayesnetworks_b200/csrc/rcpp_glue) touches it:
+// integer vectors by name (.Random.seed).  The reference's own sources do not use this.
+inline std::map<std::string, IntegerVector>& shim_globals() {
+  static std::map<std::string, IntegerVector> g;
+  return g;
+}
+class Environment {
+ public:
+  static Environment global_env() { return Environment(); }
+  bool exists(const std::string& name) const { return shim_globals().count(name) > 0; }
+  IntegerVector operator[](const std::string& name) const { return shim_globals()[name]; }
+  void assign(const std::string& name, const IntegerVector& v) const { shim_globals()[name] = v; }
+};
+
 // Rcpp::stop -> C++ exception (BEGIN_RCPP/END_RCPP turn it into an R error)
 inline void stop(const std::string& msg) { throw std::runtime_error(msg); }
 
@@ -123,6 +138,12 @@ inline void stop(const std::string& msg) { throw std::runtime_error(msg); }
 
 extern long bn_shim_rprintf_calls;
 inline void Rprintf(const char*, ...) { bn_shim_rprintf_calls++; }
+
+// R_ext/Random.h: the stand-in keeps R's generator state in the .Random.seed variable only, so
+// loading / storing it are counted no-ops.
+extern long bn_shim_rngstate_calls;
+inline void GetRNGstate() { bn_shim_rngstate_calls++; }
+inline void PutRNGstate() { bn_shim_rngstate_calls++; }
 
 // Pluggable uniform source: the driver installs the generator.
 namespace R {

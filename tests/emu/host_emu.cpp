@@ -23,12 +23,18 @@ extern "C" int emu_run_chain(
     int* final_par, int* final_npar, long* out_counters /*[12]*/) {
   ChainParams p;
   p.P = P; p.max_par = max_par; p.W = (P + 31) / 32; p.Ws = (p.W + 3) / 4 * 4; p.n_samples = n_samples;
-  p.C = C; p.ldc = P; p.node_type = node_type; p.sim_edge = sim_edge;
+  std::vector<double> diag(P);
+  for (int i = 0; i < P; i++) diag[i] = C[(size_t)i * P + i];
+  p.C = C; p.ldc = P; p.diag = diag.data(); p.node_type = node_type; p.sim_edge = sim_edge;
   p.n_sim_edges = n_sim_edges; p.phi = phi; p.omega = omega;
   p.initial_network = initial_network; p.drop = drop; p.n_iter = n_iter;
   p.output_every = output_every; p.trace_capacity = capacity; p.moves_capacity = moves_capacity;
-  p.prior_par = prior_par; p.prior_npar = prior_npar;
+  p.prior_par = prior_par; p.prior_npar = prior_npar; p.prior_stride = max_par;
   set_row_geom(p);
+  std::vector<double> ratio(max_par + 10);
+  for (int k = 0; k < (int)ratio.size(); k++) ratio[k] = (double)(n_samples - 1) / (double)(n_samples - k - 1);
+  p.sc.half_n = (double)n_samples / 2.0;
+  p.sc.ratio = ratio.data();
 
   std::vector<int> par((size_t)P * max_par), npar(P), born((size_t)P * max_par);
   std::vector<int> scratch((size_t)scratch_words(P, 1, 1)), hp_list(P);
@@ -48,11 +54,14 @@ extern "C" int emu_run_chain(
   m.npar_freq = npar_freq; m.npar_since = npar_since.data();
   std::vector<double> dscore((size_t)P * max_par, NAN);
   m.dscore = dscore.data();
+  std::vector<double> fac((size_t)P * fac_stride(fac_mp(max_par)) + 2), rowbuf((size_t)REPLAY_POS * row_stride(fac_mp(max_par)) + 2);
+  m.fac = (double*)(((uintptr_t)fac.data() + 15) & ~(uintptr_t)15);
+  m.rowbuf = (double*)(((uintptr_t)rowbuf.data() + 15) & ~(uintptr_t)15);
 
   std::vector<double> ubuf(RNG_CAP);
   RngStream rng;
   if (rng_kind == RNG_WH) rng_init_wh(rng, seeds[0], seeds[1], seeds[2], ubuf.data());
-  else if (rng_kind == RNG_RMT) rng_init_rmt(rng, mt.data(), ubuf.data());
+  else if (rng_kind == RNG_RMT) rng_init_rmt(rng, mt.data(), 624, ubuf.data());
   else rng_init_replay(rng, replay, replay_len, ubuf.data());
 
   ChainScalars s;
@@ -84,7 +93,7 @@ extern "C" void emu_uniforms(int rng_kind, const int* seeds, const unsigned int*
   if (mt_state) memcpy(mt.data(), mt_state, 624 * 4);
   RngStream rng;
   if (rng_kind == RNG_WH) rng_init_wh(rng, seeds[0], seeds[1], seeds[2], ubuf.data());
-  else rng_init_rmt(rng, mt.data(), ubuf.data());
+  else rng_init_rmt(rng, mt.data(), 624, ubuf.data());
   for (int i = 0; i < n; i++) {
     while (rng.gen_hi <= i) rng_fill_chunk(rng);
     out[i] = ubuf[i & (RNG_CAP - 1)];

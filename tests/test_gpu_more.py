@@ -207,17 +207,17 @@ def test_replay_stream_and_tabulation(dataset, oracle):
 def test_error_behaviour(dataset):
     from bayesnetworks_b200 import BnError, Context, _lib
     X, src, tgt, nt = dataset["X"], dataset["source"], dataset["target"], dataset["node_type"]
-    with pytest.raises(BnError) as ei:
-        Context.from_data(X, src, tgt, nt, max_par=3)  # node 0 has 8 parents in the prior graph
-    assert ei.value.status == _lib.BN_ERR_BAD_ARG
+    with Context.from_data(X, src, tgt, nt, max_par=3) as ctx:   # node 0 has 8 parents in the prior graph:
+        with pytest.raises(BnError) as ei:                       # fine as a prior, not as a start graph
+            ctx.run(n_iter=10, initial_network=0)
+        assert ei.value.status == _lib.BN_ERR_BAD_ARG
     with pytest.raises(BnError) as ei:
         Context.from_data(X, src, tgt, nt, max_par=200)
     assert ei.value.status == _lib.BN_ERR_UNSUPPORTED
-    with Context.from_data(X, src, tgt, nt, max_par=8) as ctx:
-        with pytest.raises(BnError) as ei:
-            ctx.run(n_iter=10, initial_network=1)
-        assert ei.value.status == _lib.BN_ERR_UNSUPPORTED
-        # every node a source: no legal addition exists -> the reference would spin forever
+    with pytest.raises(BnError) as ei:
+        Context.from_data(X, [1, 99], [2, 3], nt, max_par=8)     # edge index out of range
+    assert ei.value.status == _lib.BN_ERR_BAD_ARG
+    # every node a source: no legal addition exists -> the reference would spin forever
     all_src = np.ones_like(nt)
     with Context.from_data(X, [], [], all_src, max_par=8) as ctx:
         with pytest.raises(BnError) as ei:

@@ -269,7 +269,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.bn_abi_version() == 2
+    assert L.bn_abi_version() == 3
 
 
 def test_no_cpu_fallback():

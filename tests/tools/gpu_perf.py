@@ -23,13 +23,16 @@ if os.environ.get("H2D", "1") == "1":
         print(f"from_data (pinned) wall {1e3*(t1-t0):.1f} ms", flush=True)
 seeds = chain_seeds(chains)
 for it in [iters]:
-    t0 = time.perf_counter()
-    res, ms = ctx.run(n_chains=chains, n_iter=it, output=100, rng="wh", seeds=seeds)
-    t1 = time.perf_counter()
+    for rep in range(int(os.environ.get("REPS", 3))):   # the first launch sees the clocks ramping up
+        t0 = time.perf_counter()
+        res, ms = ctx.run(n_chains=chains, n_iter=it, output=100, rng="wh", seeds=seeds)
+        t1 = time.perf_counter()
     vi = sum(r.valid_iters for r in res); win = sum(r.windows for r in res)
     print(f"run {chains} chains x {it}: kernel {ms:.1f} ms wall {1e3*(t1-t0):.1f} ms -> {chains*it/ms/1e3:.3f} M iters/s, "
           f"{1e3*ms/it:.3f} us/iter/chain, valid {vi/(chains*it):.3f}, iters/window {chains*it/win:.1f}, "
           f"edges {np.mean([r.total_edges for r in res]):.0f}, accepted {np.mean([sum(r.proposed)-sum(r.reject[1:]) for r in res]):.0f}", flush=True)
+    kc = np.mean([r.kernel_cycles for r in res]) / it
+    print(f"kernel cycles/iter/chain {kc:.0f} (max chain {np.max([r.kernel_cycles for r in res]) / it:.0f}); implied SM clock {np.max([r.kernel_cycles for r in res]) / ms / 1e3:.0f} MHz", flush=True)
     cyc = np.array([r.phase_cycles for r in res], dtype=np.float64).mean(0)
     names = ["refill", "replayA", "scoreBC", "commit", "acc_add", "acc_del"]
     print("cycles/iter/chain: " + ", ".join(f"{n} {c/it:.0f}" for n, c in zip(names, cyc)) + f"  total {cyc.sum()/it:.0f}; slots simulated/iter {np.mean([r.slots_simulated for r in res])/it:.2f}", flush=True)
