@@ -47,14 +47,14 @@ class ChainStats(C.Structure):
     _fields_ = [("uniforms", C.c_int64), ("valid_iters", C.c_int64), ("proposed", C.c_int * 3),
                 ("reject", C.c_int * 3), ("n_nonpd", C.c_int), ("total_edges", C.c_int),
                 ("status", C.c_int), ("windows", C.c_int), ("alg_bytes", C.c_int64),
-                ("phase_cycles", C.c_int64 * 6), ("slots_simulated", C.c_int64), ("kernel_cycles", C.c_int64)]
+                ("phase_cycles", C.c_int64 * 12), ("slots_simulated", C.c_int64), ("kernel_cycles", C.c_int64)]
 
 
 import numpy as _np
 CHAIN_STATS_DTYPE = _np.dtype([("uniforms", "<i8"), ("valid_iters", "<i8"), ("proposed", "<i4", (3,)),
                                ("reject", "<i4", (3,)), ("n_nonpd", "<i4"), ("total_edges", "<i4"),
                                ("status", "<i4"), ("windows", "<i4"), ("alg_bytes", "<i8"),
-                               ("phase_cycles", "<i8", (6,)), ("slots_simulated", "<i8"), ("kernel_cycles", "<i8")],
+                               ("phase_cycles", "<i8", (12,)), ("slots_simulated", "<i8"), ("kernel_cycles", "<i8")],
                               align=True)
 assert CHAIN_STATS_DTYPE.itemsize == C.sizeof(ChainStats)
 

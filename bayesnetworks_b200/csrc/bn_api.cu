@@ -867,7 +867,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
       s.n_nonpd = res[ch].n_nonpd; s.total_edges = res[ch].total_edges; s.status = res[ch].status;
       s.windows = res[ch].windows;
       s.alg_bytes = res[ch].alg_bytes;
-      for (int t = 0; t < 6; t++) s.phase_cycles[t] = res[ch].cyc[t];
+      for (int t = 0; t < 12; t++) s.phase_cycles[t] = res[ch].cyc[t];
       s.slots_simulated = res[ch].slots_sim;
       s.kernel_cycles = res[ch].cyc_total;
     }

@@ -111,7 +111,8 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int acc_add, acc_del;  // accepted moves since `drop`: the additions / deletions columns (src/network.h:340-341)
   int gll_ok; double gll;
   int64_t alg_bytes;   // sum over scored proposals of 8*(k'+1)(k'+2)/2 + 8
-  long long cyc[6];    // cycles per phase: refill, replay (A), score (B/C), commit, accepted add, accepted delete
+  long long cyc[12];   // cycles per phase: refill, replay (A), score (B/C), commit, accepted add, accepted delete;
+                       // [6..11] split the accepted moves: list update, ancestor test, ancestor team op (add 6-8, delete 9-11)
   long long slots_sim; // iterations replayed speculatively (committed + discarded)
   int win;             // current window size
   int windows;
@@ -148,6 +149,15 @@ BN_HD long long cycle_now() {
   return 0;
 #endif
 }
+
+// counters of the ancestor updates: host emulation builds with -DBN_EMU_STATS only (tests/tools)
+#if defined(BN_EMU_STATS) && !defined(__CUDA_ARCH__)
+struct EmuStats { long del_total, del_trivial, del_desc, del_rounds, del_rows_eval, del_lost_bits, add_total, add_trivial, add_desc; };
+inline EmuStats& emu_stats() { static EmuStats s = {}; return s; }
+#define BN_STAT(x) x
+#else
+#define BN_STAT(x)
+#endif
 
 BN_HD bool test_bit(const uint32_t* row, int b) { return (row[b >> 5] >> (b & 31)) & 1u; }
 
@@ -304,6 +314,7 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
   const RowGeom g = row_geom(p);
   const int l = Warp::lane(), sub = l / g.lpr, li = l % g.lpr;
   const int n = collect_desc_part(p, m, c, 1, list, part, nparts);
+  BN_STAT(emu_stats().add_desc += n;)
   const U4* aj = (const U4*)(m.anc + (uint32_t)j * (uint32_t)p.Ws);
   if (g.chunks == 8 && Warp::NL == 32) {
     // 897..1,024 nodes: 8 lanes per row, 4 rows per pass, four passes in flight.  A pass index
@@ -390,7 +401,8 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c, int& m
     const U4* ac = (const U4*)(m.anc + (uint32_t)c * (uint32_t)p.Ws);
     int news = 0;
     for (int ch = Warp::lane(); ch < g.chunks; ch += Warp::NL) news |= nz4(andn4(aj[ch], ac[ch])) ? 1 : 0;
-    if (Warp::ballot(news) == 0u) { m_anc_changed = 0; return; }
+    BN_STAT(emu_stats().add_total++;)
+    if (Warp::ballot(news) == 0u) { BN_STAT(emu_stats().add_trivial++;) m_anc_changed = 0; return; }
   }
   m_anc_changed = 1;
 #if defined(__CUDA_ARCH__)
@@ -450,12 +462,14 @@ BN_HD DelLayout del_layout(const ChainParams& p, const ChainMem& m, int nparts) 
   return d;
 }
 
-BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts) {
+BN_HD int anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts, long long* dbg = nullptr) {
   const int l = Warp::lane(), W = p.W, MP = p.max_par;
   const DelLayout lay = del_layout(p, m, nparts);
   int* list = lay.lists + part * 2 * lay.per;
   int* list2 = list + lay.per;
+  const long long td0 = cycle_now();
   const int n = collect_desc_part(p, m, c, 0, list, part, nparts);  // old column c: rows this warp owns
+  BN_STAT(emu_stats().del_desc += n;)
   const uint32_t lt = (l == 31) ? 0x7fffffffu : ((1u << l) - 1u);
   // L is usually confined to one or two 128-bit chunks: a lane takes one (row, non-zero chunk)
   // pair, so a pass covers 32 / lpr rows with lpr = nnz rounded up to a power of two
@@ -475,8 +489,13 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
       }
     }
   }
+  const long long td1 = cycle_now();
   team_sync(m);
+  const long long td2 = cycle_now();
+  if (dbg) { dbg[6] += td1 - td0; dbg[7] += td2 - td1; }
+  int rounds_done = 0;
   for (int round = 0;; round++) {
+    const long long tr0 = cycle_now();
     const uint32_t* dprev = lay.dirty + (round % 3) * W;
     uint32_t* dnext = lay.dirty + ((round + 1) % 3) * W;
     if (part == 0) {  // nobody reads or writes these during this round
@@ -517,6 +536,7 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
       Warp::sync();
     }
     int any = 0;
+    BN_STAT(emu_stats().del_rounds++; emu_stats().del_rows_eval += nt;)
     for (int r0 = 0; r0 < nt; r0 += rpp) {
       const int r = r0 + sub;
       int changed = 0, d = 0;
@@ -553,12 +573,16 @@ BN_HD void anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part
       Warp::sync();  // later passes of this warp see the new rows
     }
     if (any && l == 0) lay.flags[round % 4] = 1;
+    const long long tr1 = cycle_now();
     team_sync(m);
+    if (dbg) { dbg[8] += tr1 - tr0; dbg[11] += cycle_now() - tr1; }
+    rounds_done++;
     if (lay.flags[round % 4] == 0) break;
   }
+  return rounds_done;
 }
 
-BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc_changed) {
+BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc_changed, long long* dbg = nullptr) {
   const RowGeom g = row_geom(p);
   const int l = Warp::lane();
   int nparts = 1;
@@ -583,9 +607,11 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc
       lay.L[ch] = lost;
       if (nz4(lost)) { ac[ch] = v; changed = 1; }
     }
-    if (Warp::ballot(changed) == 0u) { m_anc_changed = 0; return; }
+    BN_STAT(emu_stats().del_total++;)
+    if (Warp::ballot(changed) == 0u) { BN_STAT(emu_stats().del_trivial++;) m_anc_changed = 0; return; }
   }
   m_anc_changed = 1;
+  BN_STAT(for (int ch = 0; ch < g.chunks; ch++) emu_stats().del_lost_bits += popc4(lay.L[ch]);)
   for (int w = l; w < 3 * p.W + 4; w += Warp::NL) lay.dirty[w] = 0u;  // three bitsets + four flags
   Warp::sync();
   {
@@ -607,7 +633,7 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc
     if (l == 0) { m.helper[9] = c; m.helper[0] = HELPER_ANC_DEL; }
     Warp::sync();
     cta_bar(1);
-    anc_del_team(p, m, c, 0, nparts);
+    anc_del_team(p, m, c, 0, nparts, dbg);
     cta_bar(2);
     return;
   }
@@ -770,7 +796,7 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStr
   s.n_rows = 0; s.n_moves = 0; s.valid_iters = 0; s.alg_bytes = 0;
   s.gll_ok = 0; s.gll = 0.0;
   s.win = 4; s.windows = 0; s.status = 0; s.need_full = 0; s.anc_changed = 0; s.next_log = 0;
-  for (int t = 0; t < 6; t++) s.cyc[t] = 0;
+  for (int t = 0; t < 12; t++) s.cyc[t] = 0;
   s.slots_sim = 0;
 }
 
@@ -994,6 +1020,7 @@ BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars&
 struct RoundCtx {  // warp-uniform, handed to the helper warps through the command block
   int64_t pos, hi;
   int n_haspar, te_true, agree_true;
+  int redo_from;  // -1: build every record; >= 0: rebuild the deletion records from this slot on
 };
 
 // draw replay of the iteration that would start at stream position q -> record `slot`
@@ -1124,6 +1151,12 @@ BN_HD double nan_sentinel() {
 template <int KMAX>
 BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
                         WindowSlots& ws, int slot) {
+  if (rc.redo_from >= 0) {
+    // the set of nodes with parents changed: deletion draws index into it (src/network.h:311-319),
+    // so the deletion records behind the walk are replayed and decided again; additions keep theirs
+    const int old = ws.t_rec[slot];
+    if (slot < rc.redo_from || !(old & REC_TYPE) || (old & REC_OVF)) return;
+  }
   replay_position(p, m, rc.n_haspar, ubuf, rc.hi, rc.pos + slot, ws, slot);
   const int rec = ws.t_rec[slot];
   if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
@@ -1199,6 +1232,7 @@ __device__ __forceinline__ void helper_post(const ChainMem& m, int op, const Rou
     m.helper[1] = (int)(rc.pos & 0xffffffffll); m.helper[2] = (int)(rc.pos >> 32);
     m.helper[3] = (int)(rc.hi & 0xffffffffll); m.helper[4] = (int)(rc.hi >> 32);
     m.helper[5] = rc.n_haspar; m.helper[6] = rc.te_true; m.helper[7] = rc.agree_true;
+    m.helper[8] = rc.redo_from;
     m.helper[0] = op;
   }
   Warp::sync();
@@ -1208,6 +1242,7 @@ __device__ __forceinline__ RoundCtx helper_ctx(const ChainMem& m) {
   rc.pos = ((int64_t)m.helper[2] << 32) | (uint32_t)m.helper[1];
   rc.hi = ((int64_t)m.helper[4] << 32) | (uint32_t)m.helper[3];
   rc.n_haspar = m.helper[5]; rc.te_true = m.helper[6]; rc.agree_true = m.helper[7];
+  rc.redo_from = m.helper[8];
   return rc;
 }
 
@@ -1362,6 +1397,7 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     rr = ld2_l2(newrow + row_tail(fac_mp(MP)) + 2);
   }
 #endif
+  const long long tq0 = cycle_now();
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
   Warp::sync();
   if (l == 0 && m.npar_freq) {
@@ -1386,7 +1422,9 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     }
     s.te_true++; s.agree_true += ag;
     Warp::sync();
+    const long long tq1 = cycle_now();
     anc_after_add(p, m, j, c, s.anc_changed);
+    (void)tq1;
   } else {
     if (l == 0) {
       if (m.edge_freq) {
@@ -1409,7 +1447,13 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     }
     s.te_true--; s.agree_true -= ag;
     Warp::sync();
+    const long long tq1 = cycle_now();
+#if defined(BN_PHASE_CYCLES)
+    anc_after_delete(p, m, c, s.anc_changed, s.cyc);   // [6] collect+clear, [7] first barrier, [8] round work, [11] round barriers
+#else
     anc_after_delete(p, m, c, s.anc_changed);
+#endif
+    s.cyc[9] += tq1 - tq0; s.cyc[10] += cycle_now() - tq1;
   }
   if (KMAX > 8 && type == 1 && newrow) {
     const int mp = fac_mp(MP);
@@ -1624,6 +1668,7 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   RoundCtx rc;
   rc.pos = s.read_pos; rc.hi = rng.gen_hi;
   rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+  rc.redo_from = -1;
   while (s.next_log < (int)s.iter) s.next_log += p.output_every;  // (after sequential windows; else no step)
   team_records<KMAX>(p, m, rc, rng.ubuf, ws);
   long long t1 = cycle_now();
@@ -1647,14 +1692,20 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     s.slots_sim += n;
     if (stop) break;  // the next record is overflowed, stale or behind this round's positions
     if (accepted) {
-      // moves that invalidate every record: the set of nodes with parents changed (deletion
-      // draws index into it), TotalEdges < 4.  A child that reaches MaxPar only affects its own
-      // records; one that drops below it affects the draws that skipped it.
-      if (s.n_haspar != nh0 || s.te_true < 4) break;
+      // TotalEdges < 4 ends the rounds (sequential windows take over).  A child that reaches
+      // MaxPar only affects its own records; one that drops below it affects the draws that
+      // skipped it.
+      if (s.te_true < 4) break;
       if (k >= REPLAY_POS) break;
       const int unfull = (type == 2 && m.npar[c] == p.max_par - 1) ? 1 : 0;
       t0 = cycle_now();
       team_repair(p, m, ws, c, unfull, s.anc_changed, k);
+      if (s.n_haspar != nh0) {
+        // the set of nodes with parents changed: the deletion records behind the walk are redone
+        rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+        rc.redo_from = k;
+        team_records<KMAX>(p, m, rc, rng.ubuf, ws);
+      }
       s.cyc[2] += cycle_now() - t0;
     }
   }

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
     r.windows = s.windows;
     r.n_rows = s.n_rows;
     r.n_moves = s.n_moves;
-    for (int t = 0; t < 6; t++) r.cyc[t] = s.cyc[t];
+    for (int t = 0; t < 12; t++) r.cyc[t] = s.cyc[t];
     r.slots_sim = s.slots_sim;
     r.cyc_total = clk1 - clk0;
   }

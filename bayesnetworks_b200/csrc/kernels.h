@@ -44,7 +44,7 @@ struct ChainResult {
   int64_t uniforms, valid_iters, alg_bytes;
   int proposed[3], reject[3];
   int n_nonpd, total_edges, status, windows, n_rows, n_moves;
-  long long cyc[6], slots_sim, cyc_total;
+  long long cyc[12], slots_sim, cyc_total;
 };
 
 struct SweepParams {

@@ -189,9 +189,10 @@ typedef struct bn_chain_stats {
   int windows;             /* rounds (position-parallel) + sequential windows executed */
   int64_t alg_bytes;       /* sum over scored proposals of 8*(k'+1)(k'+2)/2 + 8: the algorithmic
                               gather bytes of the roofline (k' = parents in the scored set) */
-  int64_t phase_cycles[6]; /* SM cycles of the chain's warp per phase: uniform refill, position records
+  int64_t phase_cycles[12];/* SM cycles of the chain's warp per phase: uniform refill, position records
                               (draw replay + scoring), walk + repair, commit, accepted additions,
-                              accepted deletions */
+                              accepted deletions; [6..11] split the last two (list update, ancestor
+                              update, -) */
   int64_t slots_simulated; /* iterations emitted by the record walk */
   int64_t kernel_cycles;   /* SM cycles of the chain from its first to its last iteration (ABI >= 3);
                               phase_cycles are filled by diagnostics builds only (-DBN_PHASE_CYCLES) */

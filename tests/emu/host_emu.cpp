@@ -80,6 +80,15 @@ extern "C" int emu_run_chain(
   return s.status;
 }
 
+#if defined(BN_EMU_STATS)
+extern "C" void emu_get_stats(long* out) {
+  const EmuStats& s = emu_stats();
+  const long v[9] = {s.del_total, s.del_trivial, s.del_desc, s.del_rounds, s.del_rows_eval, s.del_lost_bits,
+                     s.add_total, s.add_trivial, s.add_desc};
+  for (int i = 0; i < 9; i++) out[i] = v[i];
+}
+#endif
+
 extern "C" double emu_score_set(const double* C, int P, int c, const int* S, int k, int n_samples) {
   std::vector<double> L((size_t)k * (k + 1) / 2 + 1), z(k + 1);
   int npd = 0;

@@ -34,5 +34,5 @@ for it in [iters]:
     kc = np.mean([r.kernel_cycles for r in res]) / it
     print(f"kernel cycles/iter/chain {kc:.0f} (max chain {np.max([r.kernel_cycles for r in res]) / it:.0f}); implied SM clock {np.max([r.kernel_cycles for r in res]) / ms / 1e3:.0f} MHz", flush=True)
     cyc = np.array([r.phase_cycles for r in res], dtype=np.float64).mean(0)
-    names = ["refill", "replayA", "scoreBC", "commit", "acc_add", "acc_del"]
+    names = ["refill", "records", "walk+repair", "commit", "acc_add", "acc_del", "del:collect", "del:bar0", "del:roundwork", "del:list", "del:anc", "del:roundbar"]
     print("cycles/iter/chain: " + ", ".join(f"{n} {c/it:.0f}" for n, c in zip(names, cyc)) + f"  total {cyc.sum()/it:.0f}; slots simulated/iter {np.mean([r.slots_simulated for r in res])/it:.2f}", flush=True)
