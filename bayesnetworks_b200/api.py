@@ -309,6 +309,35 @@ class Context:
         return out, float(ms.value)
 
 
+    def run_device(self, n_chains, n_iter, output, d_ints, d_gll, d_n_rows, initial_network=2, drop=0,
+                   rng="wh", seeds=None):
+        """The same chains with the trace left in HBM (``bn_run_args.device_outputs = 1``): no
+        device-to-host copy of the columns, so that they can be exchanged between GPUs directly
+        (``dist.run_sharded_device``).  ``d_ints``: device pointer of an int32 buffer
+        [7][n_chains][capacity] (columns iter, ChangedNode, movetype, additions, deletions, FN, FP),
+        ``d_gll``: float64 [n_chains][capacity], ``d_n_rows``: int32 [n_chains]; capacity =
+        ceil(n_iter / output).  Returns (stats array, kernel_ms)."""
+        L = _lib.lib()
+        cap = max(1, (n_iter + output - 1) // output)
+        col = lambda k: C.cast(C.c_void_p(int(d_ints) + 4 * k * n_chains * cap), _lib._ip)
+        tr = _lib.Trace(cap, C.cast(C.c_void_p(int(d_n_rows)), _lib._ip), col(0), col(1), col(2),
+                        C.cast(C.c_void_p(int(d_gll)), _lib._dp), col(3), col(4), col(5), col(6))
+        args = _lib.RunArgs()
+        args.n_chains, args.rng_kind = int(n_chains), int(_RNG_KINDS[rng])
+        sd = None
+        if seeds is not None:
+            sd = np.zeros((n_chains, 3), dtype=np.int32)
+            s_in = np.asarray(seeds, dtype=np.int64).reshape(n_chains, -1)
+            sd[:, :s_in.shape[1]] = s_in
+            args.seeds = sd.ctypes.data_as(_lib._ip)
+        args.initial_network, args.drop = int(initial_network), int(drop)
+        args.n_iter, args.output_every, args.device_outputs = int(n_iter), int(output), 1
+        stats = (_lib.ChainStats * n_chains)()
+        ms = C.c_float(0)
+        check(L.bn_run(self._h, C.byref(args), C.byref(tr), None, None, C.cast(stats, C.c_void_p), C.byref(ms)))
+        return np.frombuffer(stats, dtype=_lib.CHAIN_STATS_DTYPE, count=n_chains).copy(), float(ms.value)
+
+
 def block_colsum_device(data_ptr, ld, n_rows, n_nodes, out_ptr, device=0, stream=0):
     """Column sums of one row block of X (device pointers); see ``bn_block_colsum_device``."""
     check(_lib.lib().bn_block_colsum_device(C.c_void_p(int(data_ptr)), int(ld), int(n_rows), int(n_nodes),

@@ -112,6 +112,64 @@ def run_sharded(ctx, n_chains_total: int, n_iter: int, output: int, rank: int, w
     return unpack_results(gi, gg, gm), ms, local
 
 
+def run_sharded_device(ctx, n_chains_total: int, n_iter: int, output: int, rank: int, world_size: int, device,
+                       initial_network: int = 2, drop: int = 0, group=None, check: bool = True):
+    """This rank's block of chains with the traces left in HBM, then ONE exchange step: the
+    device-resident blocks are all-gathered over NCCL (NVLink) without touching the host.
+
+    Returns a dict: ``ints`` int32 [n_chains_total, capacity, 7] and ``gll`` float64
+    [n_chains_total, capacity] and ``n_rows`` int32 [n_chains_total] (CUDA tensors holding ALL
+    chains in global order, identical on every rank), ``stats`` (this rank's bn_chain_stats),
+    ``kernel_ms``, ``gather_ms`` (device time of the collectives) and ``gather_ok``: this rank's
+    own block came back unchanged at its global position and the row counts agree."""
+    import torch
+    import torch.distributed as dist
+
+    first, count = shard_chains(n_chains_total, world_size, rank)
+    counts = [shard_chains(n_chains_total, world_size, r)[1] for r in range(world_size)]
+    pad = max(counts)
+    cap = max(1, (n_iter + output - 1) // output)
+    # [7][pad][cap] so that the library's seven int columns are rows of ONE buffer
+    ints = torch.zeros((len(INT_COLUMNS), pad, cap), dtype=torch.int32, device=device)
+    gll = torch.zeros((pad, cap), dtype=torch.float64, device=device)
+    n_rows = torch.zeros((pad,), dtype=torch.int32, device=device)
+    stats, ms = None, 0.0
+    if count > 0:
+        if count != pad:   # the library lays the columns out for `count` chains: run into a view-sized buffer
+            ints_run = torch.zeros((len(INT_COLUMNS), count, cap), dtype=torch.int32, device=device)
+        else:
+            ints_run = ints
+        stats, ms = ctx.run_device(count, n_iter, output, ints_run.data_ptr(), gll.data_ptr(), n_rows.data_ptr(),
+                                   initial_network=initial_network, drop=drop, rng="wh",
+                                   seeds=chain_seeds(count, first_chain=first))
+        if ints_run is not ints:
+            ints[:, :count] = ints_run
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if world_size > 1:
+        g_ints = torch.empty((world_size,) + tuple(ints.shape), dtype=ints.dtype, device=device)
+        g_gll = torch.empty((world_size,) + tuple(gll.shape), dtype=gll.dtype, device=device)
+        g_rows = torch.empty((world_size, pad), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(g_ints, ints, group=group)
+        dist.all_gather_into_tensor(g_gll, gll, group=group)
+        dist.all_gather_into_tensor(g_rows, n_rows, group=group)
+    else:
+        g_ints, g_gll, g_rows = ints[None], gll[None], n_rows[None]
+    e1.record()
+    # global chain order (ranks own contiguous blocks; drop the padding)
+    all_ints = torch.cat([g_ints[r, :, :counts[r]] for r in range(world_size)], dim=1).permute(1, 2, 0).contiguous()
+    all_gll = torch.cat([g_gll[r, :counts[r]] for r in range(world_size)], dim=0)
+    all_rows = torch.cat([g_rows[r, :counts[r]] for r in range(world_size)], dim=0)
+    ok = True
+    if check and count > 0:
+        mine = ints[:, :count].permute(1, 2, 0)
+        ok = bool(torch.equal(all_ints[first:first + count], mine) and torch.equal(all_gll[first:first + count], gll[:count])
+                  and torch.equal(all_rows[first:first + count], n_rows[:count]))
+    torch.cuda.synchronize(device)
+    return dict(ints=all_ints, gll=all_gll, n_rows=all_rows, stats=stats, kernel_ms=ms,
+                gather_ms=float(e0.elapsed_time(e1)), gather_ok=ok, first=first, count=count)
+
+
 # ---------------------------------------------------------------------------
 # row-sharded sufficient statistics (SURVEY.md 8e)
 # ---------------------------------------------------------------------------
