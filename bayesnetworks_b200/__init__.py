@@ -10,6 +10,7 @@ from .network import Network, create_network, read_dag, read_data  # noqa: F401
 from .api import (ChainResult, Context, TRACE_COLUMNS, bn_mcmc, main_fun,  # noqa: F401
                   set_default_stream)
 from ._lib import BnError  # noqa: F401
+from .summary import summarize, summarize_result  # noqa: F401
 
 __all__ = ["Network", "create_network", "read_dag", "read_data", "Context", "ChainResult",
-           "TRACE_COLUMNS", "bn_mcmc", "main_fun", "BnError"]
+           "TRACE_COLUMNS", "bn_mcmc", "main_fun", "BnError", "summarize", "summarize_result"]

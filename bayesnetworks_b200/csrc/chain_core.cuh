@@ -1,25 +1,33 @@
-// One MCMC chain = one warp.  Replaces the loop of src/bayesnet_mcmc.cpp:45-70
-// and network::{propose_addition, propose_deletion, CheckValidity, checker,
-// LogPrior, logger} (src/network.h:254-364,415-437).
+// One MCMC chain = one CTA of eight warps, persistent for the whole run.  Replaces the loop of
+// src/bayesnet_mcmc.cpp:45-70 and network::{propose_addition, propose_deletion, CheckValidity,
+// checker, LogPrior, logger} (src/network.h:254-364,415-437).
 //
-// The reference's chain is strictly sequential, but a rejected proposal leaves
-// the graph untouched and rejections are the common case (~99% after burn-in),
-// so the warp executes a WINDOW of up to 32 consecutive iterations
-// speculatively:
-//   phase A  (warp-uniform, integer only): replay the reference's draw order
-//            for each iteration assuming all earlier ones in the window were
-//            rejected -- move type, rejection-sampled (child, parent), the
-//            acyclicity test, the stale `valid` / TotalEdges / FN / FP members
-//            (SURVEY.md Appendix A), the acceptance uniform.
-//   phase B  (one lane per iteration): score the proposed parent set with a
-//            k-dim Cholesky from the centred Gram (score_core.cuh).
-//   phase C  Hastings ratio with the reference's expression, first accepted
-//            iteration wins; everything after it is discarded and the uniform
-//            stream position rewinds to just after it.
-// The committed result is exactly the sequential one.
+// The reference's chain is strictly sequential, but the only dependences between iterations are
+// the uniform-stream position (an iteration consumes a data-dependent number of uniforms), the
+// stale `valid` flag, and the graph, which changes on the few percent of iterations that are
+// accepted.  So the chain works in ROUNDS of 256 stream positions (run_round):
+//   records   one thread per stream position q builds the record of the iteration that WOULD
+//             start at q: the reference's draw order (move type, rejection-sampled child and
+//             parent, the deletion draws), the acyclicity bit, the score of the proposed parent
+//             set and the accept decision (build_record);
+//   walk      warp 0 chases the records from the committed position (each record says how many
+//             uniforms it consumes for either value of the incoming `valid` flag), one lane per
+//             iteration, up to the first accepted one; statistics stay lane-private
+//             (round_epoch);
+//   apply     the accepted move is applied (parent list, ancestor bitsets by all eight warps) and
+//             the remaining records are REPAIRED instead of discarded: records of the changed
+//             child go stale, cycle bits are re-tested, deletion records are redone when the set
+//             of nodes with parents changed (repair_record, build_record with redo_from).
+// The committed result is exactly the sequential one (bit-identical trajectories).  Iterations
+// the records cannot represent -- `TotalEdges < 3` (src/bayesnet_mcmc.cpp:48), more than 254
+// uniforms -- take sequential windows (phase_a / phase_bc / commit); an iteration that needs more
+// uniforms than the ring holds slides the ring along (phase_a, unbounded).
 //
-// Acyclicity (pathExists, src/network.h:366-413, a BFS per proposal) is an O(1)
-// bit test against per-node ancestor bitsets, maintained on accepted moves.
+// Acyclicity (pathExists, src/network.h:366-413, a BFS per proposal) is an O(1) bit test against
+// per-node ancestor bitsets, maintained on accepted moves.
+//
+// The same source compiles for the host with a one-lane warp (tests/emu): the sequential logic is
+// checked against the oracle without a GPU.
 #pragma once
 
 #include "bn_common.cuh"
@@ -1001,7 +1009,7 @@ BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars&
 // WOULD start at q: draw replay (move type, rejection-sampled child/parent, uniforms
 // consumed, cycle test), the score of the proposed parent set, and the accept decision.
 // Roughly one position in five is a real iteration start; the rest is latency-free slack
-// of the four warps.  The chain's own warp then walks the records from the committed
+// of the eight warps.  The chain's own warp then walks the records from the committed
 // position (pointer chase over `consumed`), commits rejected iterations in bulk, and on an
 // accepted move applies it and REPAIRS the remaining records instead of discarding them:
 //   * a record depends on the graph only through its child's parent list (replay of the
@@ -1009,11 +1017,12 @@ BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars&
 //     (parent, child) pair, and the global counts TotalEdges / Nagree (prior terms);
 //   * records of the changed child are stale: the walk stops in front of the first one
 //     and the next round starts there;
-//   * cycle bits are re-tested and the accept decisions re-evaluated with the new prior
-//     terms by all threads (cyclic additions are scored too, so a bit that clears after a
-//     deletion needs no new score);
-//   * a move that changes the set of nodes with parents (deletion draws index into it) or
-//     moves the child across the MaxPar limit (child rejection loop) ends the round.
+//   * cycle bits are re-tested by all threads; the accept decisions stand (a move at another
+//     node changes the Hastings argument by rounding only; close calls are marked stale).
+//     Cyclic additions are never scored: should their cycle bit clear, the record goes stale;
+//   * a move that changes the set of nodes with parents (deletion draws index into it) has the
+//     deletion records behind the walk redone in place; a child that drops below MaxPar makes
+//     stale the draws that skipped it.
 // Requires TotalEdges >= 4 so that the `TotalEdges < 3` branch of
 // src/bayesnet_mcmc.cpp:48 cannot fire; the sequential window path covers the rest.
 // ---------------------------------------------------------------------------

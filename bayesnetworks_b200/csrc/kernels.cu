@@ -8,9 +8,12 @@
 namespace bn {
 
 // ---------------------------------------------------------------------------
-// K3: one warp (= one CTA of 32 threads) per chain, persistent for the whole run.
-// Per-chain state lives in global memory and is served from this SM's L1 (only
-// this CTA touches it); the Gram is read with L2-only loads.
+// K3: one CTA of eight warps per chain, persistent for the whole run (chain_core.cuh).  Warp 0
+// owns the chain; warps 1-7 park on a named barrier and join the team operations (position
+// records, record repair, ancestor-row updates, Wichmann-Hill refill).  The per-chain state
+// (parent lists, scores, ancestor bitsets, scratch) lives in the CTA's dynamic shared memory
+// when it fits (1,000 nodes x MaxPar 8: 202 KB), else in global memory; the Gram is read with
+// L2-only loads.
 // ---------------------------------------------------------------------------
 // ALL_SMEM: every per-chain array of the plan sits in dynamic shared memory, so the pointers
 // have a provable shared-memory provenance and the state accesses compile to LDS/STS
@@ -289,7 +292,7 @@ __device__ __forceinline__ void border_row(const double* __restrict__ C, int64_t
 }
 
 template <int KMAX, int SWEEP_WARPS>
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp) {
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, KMAX <= 8 ? 8 : 2) sweep_kernel(SweepParams sp) {
   constexpr int TRI = (KMAX + 1) * (KMAX + 2) / 2;  // augmented (k+1) lower triangle
   __shared__ double sA[SWEEP_WARPS][TRI];
   __shared__ int sS[SWEEP_WARPS][KMAX];
@@ -388,14 +391,43 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(SweepParams sp)
     if (out_s) out_s[j] = sc;
     if (out_h) out_h[j] = hr;
   }
-  // ---- deletions: one lane per current parent ----
+  // ---- deletions: one lane per current parent, O(k^2) on the shared factor ----
+  // RSS without parent e = RSS + (y'z)^2 / (y'y), y = column e of L^-1 (forward substitution from
+  // row e on): the drop-one-regressor identity instead of a fresh factorisation of S without e
+  // (erase order, src/network.h:325, changes the result by rounding only)
   for (int e = lane; e < k; e += 32) {
-    double L[KMAX * (KMAX + 1) / 2], z[KMAX];
-    int S2[KMAX];
-    int kk = 0;
-    for (int q = 0; q < k; q++) if (q != e) S2[kk++] = S[q];
-    int npd = 0;
-    const double sc = score_set(C, ldc, c, S2, kk, sp.n_samples, L, z, &npd);
+    double y[KMAX];
+    double yy, yz;
+    {
+      const double re = A[e * (e + 1) / 2 + e];  // 1 / L[e][e]
+      y[e] = re; yy = re * re; yz = re * zrow[e];
+    }
+    if constexpr (KMAX <= 16) {
+#pragma unroll
+      for (int i = 1; i < KMAX; i++) {
+        if (i > e && i < k) {
+          const double* Li = A + i * (i + 1) / 2;
+          double acc = 0.0;
+#pragma unroll
+          for (int t = 0; t < KMAX; t++)
+            if (t >= e && t < i) acc -= Li[t] * y[t];
+          acc *= Li[i];
+          y[i] = acc; yy += acc * acc; yz += acc * zrow[i];
+        }
+      }
+    } else {
+      for (int i = e + 1; i < k; i++) {
+        const double* Li = A + i * (i + 1) / 2;
+        double acc = 0.0;
+        for (int t = e; t < i; t++) acc -= Li[t] * y[t];
+        acc *= Li[i];
+        y[i] = acc; yy += acc * acc; yz += acc * zrow[i];
+      }
+    }
+    const double rss_del = rss + yz * yz / yy;
+    double sc = -(n / 2.0) * log((rss_del / (n - (double)k)) / syy);
+    // no factor of a parent Gram that is not positive definite: the reduced set is scored from scratch
+    if (!pd) sc = score_scratch<KMAX>(C, ldc, c, S, k, e, sp.n_samples, nullptr);
     const int j = S[e];
     const int a1 = sp.sim_edge[(int64_t)j + (int64_t)c * P] ? 1 : 0;
     const int te_n = te - 1, ag_n = ag - a1;

@@ -8,9 +8,13 @@
 //               centred cross-product matrix C (the intercept row/column of
 //               the reference's SXX is absorbed by the centring), through a
 //               k-dim Cholesky factor and one triangular solve -- no pass
-//               over the data, O(k^3/6) instead of O(51^3 + N k).
+//               over the data.
 //
 //   score = -(N/2) * log( [RSS/(N-k-1)] / [C_cc/(N-1)] )      (src/network.h:232-236)
+//
+// Three forms: score_set (generic, scratch arrays: score_nodes / fallbacks), score_set8
+// (MaxPar <= 8 chain kernels: the factor of the proposed set in registers) and the per-node
+// factor cache of the MaxPar > 8 chain kernels (O(k^2) per proposal, second half of this file).
 #pragma once
 
 #include "bn_common.cuh"

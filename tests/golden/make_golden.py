@@ -14,6 +14,8 @@ Writes (all small, committed):
         (oracle/_ref/libbnref.so, oracle/_ref/legacy_main): RNG known answers,
         sufficient statistics, per-node scores, traces for configs 1 and 2,
         a per-iteration (output=1) trace, InvertPDS samples.
+  tests/golden/legacy_summary.txt, legacy_edges.txt   networks-summary.txt / networks-edges.txt written by
+        the reference's legacy program (oracle/_ref/legacy_main) on its own input.
   tests/golden/legacy_xlsx.npz      the reference's own golden trace
         `Bayes-networks/iterations - null start.xlsx` (1,100 rows) parsed to arrays.
 
@@ -147,6 +149,11 @@ def main():
         env = dict(os.environ, BN_LEGACY_IN=BN, BN_LEGACY_OUT=td)
         subprocess.check_call([LEGACY_BIN], env=env, stdout=subprocess.DEVNULL)
         lines = [ln.split() for ln in open(os.path.join(td, "networks-iterations.txt")) if ln.strip()][1:]
+        # Summarize() output of the same run (main.cpp:299-339): pins the report format of
+        # bayesnetworks_b200/summary.py
+        import shutil
+        shutil.copy(os.path.join(td, "networks-summary.txt"), os.path.join(HERE, "legacy_summary.txt"))
+        shutil.copy(os.path.join(td, "networks-edges.txt"), os.path.join(HERE, "legacy_edges.txt"))
     assert len(lines) == len(body) == 1100
     for ln, r in zip(lines, body):
         assert int(ln[0]) == int(r[0]) and int(ln[1]) == int(r[1]) and int(ln[11]) == int(r[11])

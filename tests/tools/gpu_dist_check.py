@@ -45,9 +45,28 @@ if 8 % world == 0:
         c1.close()
         ok &= bool(torch.equal(gram_s, gram_1)) and bool(torch.equal(mean_s, mean_1))
         ok &= bool(np.array_equal(r_sh.trace["globalLL"], r_1.trace["globalLL"]))
+# device-resident traces exchanged over NCCL without host staging (what bench.py times for N > 1)
+from bayesnetworks_b200.dist import run_sharded_device
+with Context.from_data(z["X"], z["source"], z["target"], z["node_type"], max_par=8, device=local) as ctx:
+    out = run_sharded_device(ctx, n_chains, n_iter, output, rank, world, dev)
+    ok &= bool(out["gather_ok"])
+    for c in range(n_chains):   # every rank holds every chain's trace, equal to the host-staged gather
+        rows = int(out["n_rows"][c].item())
+        ok &= rows == len(allres[c]["trace"]["iter"])
+        for k, name in enumerate(INT_COLUMNS):
+            ok &= bool(np.array_equal(out["ints"][c, :rows, k].cpu().numpy(), allres[c]["trace"][name]))
+        ok &= bool(np.array_equal(out["gll"][c, :rows].cpu().numpy(), allres[c]["trace"]["globalLL"]))
+    gather_ms = out["gather_ms"]
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"dist check world={world} chains={n_chains}: {'OK' if t.item() == 1 else 'FAILED'}", flush=True)
+    msg = (f"dist check world={world} chains={n_chains} (uneven blocks): chains sharded by global index, host-staged "
+           f"and device-resident NCCL all-gather, row-sharded Gram vs single GPU: {'OK' if t.item() == 1 else 'FAILED'}"
+           f" (device gather {gather_ms:.3f} ms)")
+    print(msg, flush=True)
+    out_dir = os.path.join(os.path.dirname(__file__), "..", "..", "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, f"dist_check_n{world}.txt"), "w") as fh:
+        fh.write(msg + "\n")
 dist.destroy_process_group()
 sys.exit(0 if t.item() == 1 else 1)
