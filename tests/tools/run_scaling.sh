@@ -1,5 +1,5 @@
 # usage: bash tests/tools/run_scaling.sh <max_gpus> [tag]   (run under gpurun --gpus <max_gpus>)
-MAXG=${1:-8}; TAG=${2:-r1}
+MAXG=${1:-8}; TAG=${2:-r2}
 for n in 1 2 4 8; do
   [ $n -gt $MAXG ] && break
   if [ $n -eq 1 ]; then
@@ -10,6 +10,3 @@ for n in 1 2 4 8; do
   echo "n=$n rc=$?"; tail -1 gpurun_out/scale_${TAG}_n$n.json | cut -c1-250
 done
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $MAXG --master-addr 127.0.0.1 --master-port 29700 tests/tools/gpu_dist_check.py 2>&1 | tail -2
-# BASELINE.json configs[4]: 5,000 x 1,000,000, 512 chains, sample axis and chains sharded over the GPUs
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $MAXG --master-addr 127.0.0.1 --master-port 29710 tests/tools/gpu_config5.py > gpurun_out/config5_${TAG}_n$MAXG.json 2> gpurun_out/config5_${TAG}_n$MAXG.err
-echo "config5 rc=$?"; tail -1 gpurun_out/config5_${TAG}_n$MAXG.json
