@@ -511,49 +511,6 @@ BN_HD int anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part,
       for (int w = l; w < W; w += Warp::NL) dclr[w] = 0u;
       if (l == 0) lay.flags[(round + 2) % 4] = 0;
     }
-    int any = 0;
-    if (MP <= 8 && nnz <= 8 && Warp::NL == 32) {
-      // One lane per descendant (the usual case on the device: the warp's ~n/8 rows in one pass).
-      // A row is evaluated when a parent regained a bit last round (every row in round 0), and
-      // only in the chunks where it still misses bits of L: a row that has everything back costs
-      // its own chunks only.  All loads of a row are independent: one latency chain per pass.
-      for (int i0 = 0; i0 < n; i0 += Warp::NL) {
-        const int i = i0 + l;
-        const int d = (i < n) ? list[i] : -1;
-        int changed = 0;
-        if (d >= 0) {
-          const Par8 pq = load_par8(p, m, d);
-          int touched = (round == 0) ? 1 : 0;
-          if (round > 0) {
-#pragma unroll
-            for (int e = 0; e < 8; e++)
-              if (pq.q[e] >= 0) touched |= (dprev[pq.q[e] >> 5] >> (pq.q[e] & 31)) & 1u;
-          }
-          if (touched) {
-            U4* ad = (U4*)(m.anc + (uint32_t)d * (uint32_t)p.Ws);
-            for (int t = 0; t < nnz; t++) {
-              const int ch = lay.nzc[1 + t];
-              const U4 cur = ad[ch];
-              const U4 miss = andn4(lay.L[ch], cur);
-              if (nz4(miss)) {
-                U4 v = {0u, 0u, 0u, 0u};
-#pragma unroll
-                for (int e = 0; e < 8; e++) {
-                  const int q = pq.q[e];
-                  if (q >= 0) v = or4(v, ((const U4*)(m.anc + (uint32_t)q * (uint32_t)p.Ws))[ch]);
-                }
-                const U4 gain = and4(v, miss);
-                if (nz4(gain)) { ad[ch] = or4(cur, gain); changed = 1; }
-              }
-            }
-          }
-        }
-        if (changed) atomic_or_u32(&dnext[d >> 5], 1u << (d & 31));
-        any |= (Warp::ballot(changed) != 0u);
-        Warp::sync();
-      }
-      BN_STAT(emu_stats().del_rounds++;)
-    } else {
     const int* rows = list;
     int nt = n;
     if (round > 0) {
@@ -586,6 +543,7 @@ BN_HD int anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part,
       }
       Warp::sync();
     }
+    int any = 0;
     BN_STAT(emu_stats().del_rounds++; emu_stats().del_rows_eval += nt;)
     for (int r0 = 0; r0 < nt; r0 += rpp) {
       const int r = r0 + sub;
@@ -621,7 +579,6 @@ BN_HD int anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part,
       if (r < nt && li == 0 && (mask & gm)) atomic_or_u32(&dnext[d >> 5], 1u << (d & 31));
       any |= (mask != 0u);
       Warp::sync();  // later passes of this warp see the new rows
-    }
     }
     if (any && l == 0) lay.flags[round % 4] = 1;
     const long long tr1 = cycle_now();
