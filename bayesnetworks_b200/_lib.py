@@ -75,7 +75,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("BN_B200_LIB") or _build.LIB   # (BN_B200_LIB: another build of the same library, for A/B runs)
     if not os.path.exists(path):
         _build.build()
     L = C.CDLL(path)

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "chain_core.cuh"
 #include "kernels.h"
 
@@ -347,6 +349,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, KMAX <= 8 ? 8 : 2) sweep_ker
   const double rss = A[tri - 1];
   const double add_scale = 1.0 / ((n - (double)k - 2.0) * syy);  // 1 / (dof * SYY) of an addition
   const double* zrow = A + k * (k + 1) / 2;
+  if (!(rss > Ccc * RSS_FLOOR)) pd = false;
   const double base = pd ? -(n / 2.0) * log((rss / (n - (double)k - 1.0)) / syy) : -INFINITY;
   if (lane == 0 && sp.out_base) sp.out_base[wg] = base;
 
@@ -364,32 +367,73 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, KMAX <= 8 ? 8 : 2) sweep_ker
   double* out_h = sp.out_log_hr ? sp.out_log_hr + wg * P : nullptr;
 
   // ---- additions: lanes sweep j ----
-  for (int j0 = 0; j0 < P; j0 += 32) {
-    const int j = j0 + lane;
-    if (j >= P) break;
-    bool member = false;
-    for (int e = 0; e < k; e++) member |= (S[e] == j);
-    if (member) continue;  // deletions below
-    double sc = nan, hr = nan;
-    if (can_add && j != c && sp.node_type[j] != 2) {
-      const int a1 = sim_row[j];
-      if (!pd) {
-        sc = -INFINITY;
-      } else {
-        double dj = sp.diag[j];
-        double ej = __ldcg(C + (int64_t)c * ldc + j);
-        border_row<KMAX>(C, ldc, S, k, j, A, zrow, dj, ej);
-        if (dj > 0.0) {
-          const double rss_new = rss - ej * ej / dj;
-          sc = -(n / 2.0) * log(rss_new * add_scale);
-        } else {
-          sc = -INFINITY;
-        }
-      }
-      hr = sub_rn(add_rn(sub_rn(sc, base), a1 ? add_prior1 : add_prior0), old_prior);
+  // The loop is specialised on the number of current parents (a compile-time KK up to 8: the border
+  // row unrolls without guards and the parent list sits in registers); larger sets take the generic
+  // form.  `KK < 0` = generic.
+  auto sweep_adds = [&](auto kk_tag) {
+    constexpr int KK = decltype(kk_tag)::value;
+    int Sr[KK > 0 ? KK : 1];
+    if constexpr (KK > 0) {
+#pragma unroll
+      for (int e = 0; e < KK; e++) Sr[e] = S[e];
     }
-    if (out_s) out_s[j] = sc;
-    if (out_h) out_h[j] = hr;
+    for (int j0 = 0; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      if (j >= P) break;
+      bool member = false;
+      if constexpr (KK >= 0) {
+#pragma unroll
+        for (int e = 0; e < KK; e++) member |= (Sr[e] == j);
+      } else {
+        for (int e = 0; e < k; e++) member |= (S[e] == j);
+      }
+      if (member) continue;  // deletions below
+      double sc = nan, hr = nan;
+      if (can_add && j != c && sp.node_type[j] != 2) {
+        const int a1 = sim_row[j];
+        if (!pd) {
+          sc = -INFINITY;
+        } else {
+          double dj = sp.diag[j];
+          double ej = __ldcg(C + (int64_t)c * ldc + j);
+          if constexpr (KK >= 0) {
+            double g[KK > 0 ? KK : 1], w[KK > 0 ? KK : 1];
+#pragma unroll
+            for (int i = 0; i < KK; i++) g[i] = __ldcg(C + (int64_t)Sr[i] * ldc + j);
+#pragma unroll
+            for (int i = 0; i < KK; i++) {
+              double acc = g[i];
+#pragma unroll
+              for (int t = 0; t < i; t++) acc -= A[i * (i + 1) / 2 + t] * w[t];
+              acc *= A[i * (i + 1) / 2 + i];  // the diagonal slot holds 1 / L[i][i]
+              w[i] = acc;
+              dj -= acc * acc;
+              ej -= acc * zrow[i];
+            }
+          } else {
+            border_row<KMAX>(C, ldc, S, k, j, A, zrow, dj, ej);
+          }
+          const double rss_new = rss - ej * ej / dj;
+          if (dj > 0.0 && rss_new > Ccc * RSS_FLOOR) sc = -(n / 2.0) * log(rss_new * add_scale);
+          else sc = -INFINITY;   // not positive definite / an exact fit the Gram route cannot resolve
+        }
+        hr = sub_rn(add_rn(sub_rn(sc, base), a1 ? add_prior1 : add_prior0), old_prior);
+      }
+      if (out_s) out_s[j] = sc;
+      if (out_h) out_h[j] = hr;
+    }
+  };
+  switch (k) {
+    case 0: sweep_adds(std::integral_constant<int, 0>{}); break;
+    case 1: sweep_adds(std::integral_constant<int, 1>{}); break;
+    case 2: sweep_adds(std::integral_constant<int, 2>{}); break;
+    case 3: sweep_adds(std::integral_constant<int, 3>{}); break;
+    case 4: sweep_adds(std::integral_constant<int, 4>{}); break;
+    case 5: sweep_adds(std::integral_constant<int, 5>{}); break;
+    case 6: sweep_adds(std::integral_constant<int, 6>{}); break;
+    case 7: sweep_adds(std::integral_constant<int, 7>{}); break;
+    case 8: sweep_adds(std::integral_constant<int, 8>{}); break;
+    default: sweep_adds(std::integral_constant<int, -1>{}); break;
   }
   // ---- deletions: one lane per current parent, O(k^2) on the shared factor ----
   // RSS without parent e = RSS + (y'z)^2 / (y'y), y = column e of L^-1 (forward substitution from

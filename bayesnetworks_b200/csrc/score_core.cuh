@@ -21,6 +21,13 @@
 
 namespace bn {
 
+// A residual sum of squares at or below this fraction of C_cc is rounding noise of the Gram route
+// (the parent set reproduces the child exactly): the set is treated like a parent Gram that is not
+// positive definite -- score -inf, counted in n_nonpd -- instead of letting a zero or negative RSS
+// put a NaN into the node's score (which would accept every later proposal at that node,
+// `runif > NaN` being false).  The reference's data pass gives a tiny positive RSS there and accepts.
+constexpr double RSS_FLOOR = 1e-13;
+
 // L: k*(k+1)/2 scratch (row-packed lower triangle), z: k scratch.
 // Returns -inf and sets *nonpd when a pivot is <= 0 (the reference only
 // prints in that case, src/network.h:213-215; see DESIGN.md "deviations").
@@ -57,6 +64,10 @@ BN_HD double score_set(const double* __restrict__ C, int64_t ldc, int c,
     acc = acc / d;
     z[i] = acc;
     rss -= acc * acc;
+  }
+  if (!(rss > Ccc * RSS_FLOOR)) {
+    if (nonpd) *nonpd = 1;
+    return -INFINITY;
   }
   const double resid2 = rss / (double)(n_samples - k - 1);
   const double syy = Ccc / (double)(n_samples - 1);
@@ -122,7 +133,7 @@ BN_HD double score_set_small(const double* __restrict__ C, int64_t ldc, int c, c
       rss -= acc * acc;
     }
   }
-  if (bad) {
+  if (bad || !(rss > Ccc * RSS_FLOOR)) {
     if (nonpd) *nonpd = 1;
     return -INFINITY;
   }
@@ -235,6 +246,10 @@ BN_NOINLINE double factor_node(const double* C, int64_t ldc, int c, const int* S
     z[i] = acc;
     rss -= acc * acc;
   }
+  if (!(rss > Ccc * RSS_FLOOR)) {
+    F[fac_tail(mp)] = NAN; F[fac_tail(mp) + 1] = icc;
+    return -INFINITY;
+  }
   F[fac_tail(mp)] = rss; F[fac_tail(mp) + 1] = icc;
   return score_from_rss(rss, icc, k, sc);
 }
@@ -281,6 +296,7 @@ BN_NOINLINE double factor_node8(const double* C, int64_t ldc, int c, Parents8 S,
     }
   }
   const double icc = 1.0 / Ccc;
+  if (!(rss > Ccc * RSS_FLOOR)) bad = true;
   const int nrow = fac_row(k);
 #pragma unroll
   for (int q = 0; q < fac_row(K) / 2; q++)
@@ -326,8 +342,9 @@ BN_NOINLINE double score_move_stream(const double* C, int64_t ldc, const double*
       dj -= a * a;
       ej -= a * ld1_l2(z + i);
     }
-    const bool bad = !(rss == rss) || !(dj > 0.0);
-    const double rss_new = bad ? NAN : rss - ej * ej / dj;
+    bool bad = !(rss == rss) || !(dj > 0.0);
+    double rss_new = bad ? NAN : rss - ej * ej / dj;
+    if (!bad && !(rss_new * icc > RSS_FLOOR)) { bad = true; rss_new = NAN; }
     if (rowout) {
       for (int t = 0; t < k; t++) rowout[t] = w[t];
       rowout[row_tail(mp)] = dj; rowout[row_tail(mp) + 1] = ej; rowout[row_tail(mp) + 2] = rss_new;
@@ -413,10 +430,10 @@ BN_NOINLINE double score_move8(const double* C, int64_t ldc, const double* diag,
     yz += a * z[i];
   }
   const bool nofac = !(rss == rss);
-  const bool bad = add && (nofac || !(dj > 0.0));
   const double num = add ? ej * ej : yz * yz, den = add ? dj : yy;
   const double q = num / den;
   const double rss_new = add ? rss - q : rss + q;
+  const bool bad = add && (nofac || !(dj > 0.0) || !(rss_new * icc > RSS_FLOOR));
   if (add && rowout) {
 #pragma unroll
     for (int t = 0; t < K / 2; t++) { D2 v; v.x = w[2 * t]; v.y = w[2 * t + 1]; *(D2*)(rowout + 2 * t) = v; }

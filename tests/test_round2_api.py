@@ -200,3 +200,42 @@ def test_gpu_few_samples_with_default_maxpar(oracle):
     with Context.from_data(X, g.source, g.target, nt, max_par=50) as ctx:
         r = ctx.run(n_iter=2000, output=10, rng="wh", log_moves=True)[0][0]
     _same_trace(r, ref, 45)
+
+
+def collinear_case():
+    """Column 7 is an exact copy of column 3 and column 11 an exact linear combination of 2 and 5:
+    parent sets containing such a pair have a singular Gram, and a node regressed on its own copy
+    has RSS = 0."""
+    X, g, nt = synthetic(24, 400, 8, 55)
+    X = np.array(X)
+    X[:, 7] = X[:, 3]
+    X[:, 11] = 0.5 * X[:, 2] - 1.5 * X[:, 5]
+    nt = np.zeros_like(nt)
+    return np.asfortranarray(X), g, nt
+
+
+def test_chain_core_host_build_collinear_columns(emu_lib):
+    """Degenerate data: exact fits / singular parent sets are refused and counted, the
+    node scores stay finite -- no NaN that would accept everything afterwards."""
+    from test_host_logic import _emu_run
+    X, g, nt = collinear_case()
+    r = _emu_run(emu_lib, dict(X=X, source=g.source, target=g.target, node_type=nt), 8, 20000, 10, 0, (3, 4, 5), omega=0.5)
+    assert r["rc"] == 0 and int(r["cnt"][10]) > 0
+    assert np.isfinite(r["globalLL"]).all()
+    for c in (3, 7):
+        ps = set(int(q) for q in r["fpar"][c, :r["fnpar"][c]])
+        assert not ({3, 7} - {c}) & ps   # a column is never regressed on its own copy
+
+
+@pytest.mark.gpu
+def test_gpu_collinear_columns_are_flagged():
+    from bayesnetworks_b200 import Context
+    X, g, nt = collinear_case()
+    with Context.from_data(X, g.source, g.target, nt, max_par=8, omega=0.5) as ctx:
+        res, _ = ctx.run(n_chains=2, n_iter=20000, output=10, rng="wh", seeds=[(3, 4, 5), (6, 7, 8)])
+        for r in res:
+            assert r.n_nonpd > 0 and np.isfinite(r.trace["globalLL"]).all()
+            for c in (3, 7):
+                assert not ({3, 7} - {c}) & set(int(q) for q in r.final_parents[c, :r.final_npar[c]])
+        base, score, hr = ctx.score_all_proposals(res[0].final_parents, res[0].final_npar)
+        assert np.isfinite(base).all() and score[0, 3, 7] == -np.inf and score[0, 7, 3] == -np.inf
