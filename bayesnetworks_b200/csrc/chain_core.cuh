@@ -1157,15 +1157,147 @@ BN_HD double nan_sentinel() {
 #endif
 }
 
+// Warp-cooperative O(k^2) scoring of ONE proposal at a node with 9..32 parents (MaxPar > 8 kernels,
+// device only).  A single thread streaming the node's factor pays an L2 round trip per row, and the
+// slowest record sets the length of a round; here lane l owns row l of the factor (its entries in
+// registers, every load of the warp in flight at once) and the forward substitution runs across
+// the lanes: step t finalises w_t on lane t, broadcasts it, and the lanes below subtract their
+// L[l][t] w_t.  Same arithmetic as score_move_stream up to the order of the two final sums.
+// All 32 lanes call it with the same arguments.
+#if defined(__CUDACC__)
+template <int KMAX>
+__device__ __forceinline__ double coop_score(const ChainParams& p, const ChainMem& m, int c, int j, int type, int del,
+                                             double* rowout, int* npd) {
+  const int l = Warp::lane(), MP = p.max_par, mp = fac_mp(MP);
+  const double* F = m.fac + (int64_t)c * fac_stride(mp);
+  const int k = m.npar[c];
+  const bool mine = l < k;
+  const double* Frow = F + fac_row(l);
+  D2 r[16];  // own row: L[l][0..l-1] (the reciprocal pivot is read separately)
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    r[q].x = 0.0; r[q].y = 0.0;
+    if (mine && 2 * q < l) r[q] = ld2_l2(Frow + 2 * q);
+  }
+  const double rinv = mine ? ld1_l2(Frow + l) : 0.0;
+  const double zl = mine ? ld1_l2(F + fac_zoff(mp) + l) : 0.0;
+  const D2 tail = ld2_l2(F + fac_tail(mp));
+  const double rss = tail.x, icc = tail.y;
+  const bool add = type == 1;
+  double a = 0.0, d0 = 0.0, e0 = 0.0;
+  if (add) {
+    if (mine) a = ld_shared_ro(p.C + (int64_t)m.par[(int64_t)c * MP + l] * p.ldc + j);
+    d0 = ld_shared_ro(p.diag + j);
+    e0 = ld_shared_ro(p.C + (int64_t)c * p.ldc + j);
+  }
+  double w_own = 0.0;
+#pragma unroll
+  for (int t = 0; t < 32; t++) {
+    if (t < k) {  // (warp-uniform)
+      const double cand = (!add && l == del) ? rinv : a * rinv;  // deletion: y_del = 1 / L[del][del], y_t = 0 above it
+      const double wt = Warp::shfl(cand, t);
+      if (l == t) w_own = wt;
+      const double lt = (t & 1) ? r[t >> 1].y : r[t >> 1].x;  // L[l][t] (0 unless t < l)
+      if (l > t) a -= lt * wt;
+    }
+  }
+  const double s1 = Warp::sum(w_own * w_own), s2 = Warp::sum(w_own * zl);
+  *npd = 0;
+  if (add) {
+    const double dj = d0 - s1, ej = e0 - s2;
+    bool bad = !(rss == rss) || !(dj > 0.0);
+    double rss_new = bad ? NAN : rss - ej * ej / dj;
+    if (!bad && !(rss_new * icc > RSS_FLOOR)) { bad = true; rss_new = NAN; }
+    if (rowout) {
+      if (mine) rowout[l] = w_own;
+      if (l == 0) { rowout[row_tail(mp)] = dj; rowout[row_tail(mp) + 1] = ej; rowout[row_tail(mp) + 2] = rss_new; }
+    }
+    if (bad) { *npd = 1; return -INFINITY; }
+    return score_from_rss(rss_new, icc, k + 1, p.sc);
+  }
+  return score_from_rss(rss + s2 * s2 / s1, icc, k - 1, p.sc);
+}
+#endif
+
+#if defined(__CUDACC__)
+template <int KMAX>
+__device__ __forceinline__ void build_record_coop(const ChainParams& p, const ChainMem& m, const RoundCtx& rc,
+                                                  const double* ubuf, WindowSlots& ws, int slot, bool active) {
+  // (`active` false: this thread has no record to build in this call but takes part in the
+  // cooperative scoring of its warp)
+  int rec = 0, skip = 1, kk = 0, npd = 0, ag = 0, need = 0, big = 0, c = 0, j = 0, e = -1, type = 1;
+  double sc = 0.0, cached = nan_sentinel();
+  double* cache = nullptr;
+  double* rowout = m.rowbuf + (uint32_t)slot * (uint32_t)row_stride(fac_mp(p.max_par));
+  if (active) {
+    replay_position(p, m, rc.n_haspar, ubuf, rc.hi, rc.pos + slot, ws, slot);
+    rec = ws.t_rec[slot];
+    if (rec & REC_OVF) {
+      ws.t_walk[slot] = WALK_OVF;
+    } else if (!(rec & REC_TYPE) && (rec & REC_CYC)) {
+      ws.t_rec[slot] = rec | REC_NOSCORE;  // a cyclic addition is never scored (build_record)
+      decide_record(p, m, rc, ubuf, ws, slot);
+    } else {
+      skip = 0;
+      c = ws.t_c[slot]; j = ws.t_j[slot]; e = ws.t_e[slot];
+      type = (rec & REC_TYPE) ? 2 : 1;
+      cache = (m.dscore && (rec & REC_TYPE)) ? m.dscore + (uint32_t)c * (uint32_t)p.max_par + e : nullptr;
+      if (cache) cached = ld_shared_ro(cache);
+      ag = ld_shared_ro(p.sim_edge + (int64_t)j + (int64_t)c * p.P) ? REC_AG : 0;
+      ws.t_lu[slot] = log(ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)]);
+      if (cached == cached) {
+        sc = cached;
+        kk = m.npar[c] - 1;
+        npd = (sc == -INFINITY) ? 1 : 0;
+      } else {
+        need = 1;
+        const int k = m.npar[c];
+        // nodes with 9..32 parents whose block holds a factor: scored by the whole warp below
+        big = (k > 8 && k <= 32 && ld1_l2(m.fac + (int64_t)c * fac_stride(fac_mp(p.max_par)) + fac_tail(fac_mp(p.max_par))) ==
+                                       ld1_l2(m.fac + (int64_t)c * fac_stride(fac_mp(p.max_par)) + fac_tail(fac_mp(p.max_par)))) ? 1 : 0;
+        if (!big) sc = score_proposal<KMAX>(p, m, type, c, j, e, rowout, &kk, &npd);
+      }
+    }
+  }
+  uint32_t todo = Warp::ballot(big);
+  while (todo) {
+    const int src = ffs32(todo) - 1;
+    todo &= todo - 1;
+    const int b_c = Warp::shfl(c, src), b_j = Warp::shfl(j, src), b_type = Warp::shfl(type, src), b_e = Warp::shfl(e, src);
+    const int b_slot = Warp::shfl(slot, src);
+    int b_npd = 0;
+    const double v = coop_score<KMAX>(p, m, b_c, b_j, b_type, b_e,
+                                      m.rowbuf + (uint32_t)b_slot * (uint32_t)row_stride(fac_mp(p.max_par)), &b_npd);
+    if (Warp::lane() == src) { sc = v; npd = b_npd; kk = m.npar[c] + (type == 1 ? 1 : -1); }
+  }
+  if (active && !skip) {
+    if (need && cache) *cache = sc;  // (duplicates within a round store the same value)
+    ws.t_score[slot] = sc;
+    ws.t_rec[slot] = rec | ag | (npd ? REC_NPD : 0) | (kk << REC_KK_SHIFT);
+    decide_record(p, m, rc, ubuf, ws, slot);
+  }
+}
+#endif
+
 template <int KMAX>
 BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
                         WindowSlots& ws, int slot) {
+  bool active = true;
   if (rc.redo_from >= 0) {
     // the set of nodes with parents changed: deletion draws index into it (src/network.h:311-319),
     // so the deletion records behind the walk are replayed and decided again; additions keep theirs
     const int old = ws.t_rec[slot];
-    if (slot < rc.redo_from || !(old & REC_TYPE) || (old & REC_OVF)) return;
+    if (slot < rc.redo_from || !(old & REC_TYPE) || (old & REC_OVF)) active = false;
   }
+#if defined(__CUDA_ARCH__)
+  if constexpr (KMAX > 8) {
+    // MaxPar > 8 on the device: the same record, written without early exits so that the whole warp
+    // reaches the cooperative scoring of the proposals at nodes with 9..32 parents
+    build_record_coop<KMAX>(p, m, rc, ubuf, ws, slot, active);
+    return;
+  }
+#endif
+  if (!active) return;
   replay_position(p, m, rc.n_haspar, ubuf, rc.hi, rc.pos + slot, ws, slot);
   const int rec = ws.t_rec[slot];
   if (rec & REC_OVF) { ws.t_walk[slot] = WALK_OVF; return; }
@@ -1445,8 +1577,14 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
         for (int e = del; e + 1 < k; e++) bc[e] = bc[e + 1];
       pc[k - 1] = -1;
       m.npar[c] = k - 1;
-      // (MaxPar > 8: later proposals at c are compared with the score of the new factor)
-      m.base[c] = KMAX > 8 ? factor_current<KMAX>(p, m, c) : new_score;
+      // MaxPar > 8: the node's factor follows by a Givens downdate (a fresh factorisation when the
+      // block holds none); later proposals at c are compared with the score of the new factor
+      if (KMAX > 8) {
+        const double rss_old = F[fac_tail(fac_mp(MP))];
+        m.base[c] = (rss_old == rss_old) ? factor_downdate<KMAX>(F, k, del, p.sc, fac_mp(MP)) : factor_current<KMAX>(p, m, c);
+      } else {
+        m.base[c] = new_score;
+      }
     }
     if (k == 1) {
       Warp::sync();

@@ -309,20 +309,62 @@ BN_NOINLINE double factor_node8(const double* C, int64_t ldc, int c, Parents8 S,
   return bad ? -INFINITY : score_from_rss(rss, icc, k, sc);
 }
 
+// Accepted deletion of the parent in slot e: the factor of the reduced (order-preserving) list by
+// Givens rotations instead of a fresh O(k^3) factorisation.  Dropping row e of L leaves a
+// (k-1) x k matrix with one super-diagonal from row e on; rotating the column pairs (t, t+1),
+// t = e..k-2, makes it lower triangular again (the last column becomes zero).  z takes the same
+// rotations; its last component leaves the regression: rss' = rss + zeta^2.  Rows below e are
+// untouched.  One lane, in place in the node's block; O((k - e)^2).  Returns the new score.
+// The block must hold a valid factor (rss not NaN).
+template <int KMAX>
+BN_NOINLINE double factor_downdate(double* F, int k, int e, ScoreConsts sc, int mp) {
+  double cs[KMAX], sn[KMAX], x[KMAX + 1];
+  double* z = F + fac_zoff(mp);
+  for (int i = e; i + 1 < k; i++) {  // new row i = old row i + 1
+    const int r = i + 1;
+    const double* Lr = F + fac_row(r);
+    for (int t = 0; t < r; t++) x[t] = Lr[t];
+    x[r] = 1.0 / Lr[r];  // the diagonal slot holds the reciprocal pivot
+    for (int t = e; t < i; t++) {  // the rotations defined by the rows above
+      const double a = x[t], b = x[t + 1];
+      x[t] = cs[t] * a + sn[t] * b;
+      x[t + 1] = cs[t] * b - sn[t] * a;
+    }
+    const double a = x[i], b = x[i + 1];  // b: the old pivot, > 0
+    const double rinv = rsqrt_f64(a * a + b * b);
+    cs[i] = a * rinv; sn[i] = b * rinv;
+    double* Li = F + fac_row(i);
+    for (int t = 0; t < i; t++) Li[t] = x[t];
+    Li[i] = rinv;
+  }
+  double zt = z[e];
+  for (int t = e; t + 1 < k; t++) {
+    const double a = zt, b = z[t + 1];
+    z[t] = cs[t] * a + sn[t] * b;
+    zt = cs[t] * b - sn[t] * a;
+  }
+  const double rss = F[fac_tail(mp)] + zt * zt, icc = F[fac_tail(mp) + 1];
+  F[fac_tail(mp)] = rss;
+  return score_from_rss(rss, icc, k - 1, sc);
+}
+
 // flags of the proposal scorers
 enum { SCORE_NPD = 1,      // addition: the enlarged parent Gram is not positive definite (score -inf)
        SCORE_NOFACTOR = 2  // deletion: the current block is marked not positive definite; the caller
                            // scores the reduced set from scratch
 };
 
-// Generic MaxPar: the block is streamed row by row, w[] / y[] are the only arrays.
+// Generic MaxPar: w[] / y[] are the only arrays; the block is read row by row, either straight from
+// L2 (LOCAL = false) or from a private copy (LOCAL = true, see score_move_staged).
 // type 1: score of S + [j] (rowout receives the candidate row); type 2: score of S without slot del.
-template <int KMAX>
-BN_NOINLINE double score_move_stream(const double* C, int64_t ldc, const double* diag, int c, const int* S, int k,
-                                     int type, int j, int del, ScoreConsts sc, const double* F, int mp,
-                                     double* rowout, int* flags) {
+template <int KMAX, bool LOCAL>
+BN_HD double score_move_rows(const double* C, int64_t ldc, const double* diag, int c, const int* S, int k,
+                             int type, int j, int del, ScoreConsts sc, const double* F, int mp, int mp_row,
+                             double* rowout, int* flags) {
+  auto LD2 = [](const double* q) -> D2 { if (LOCAL) return *(const D2*)q; return ld2_l2(q); };
+  auto LD1 = [](const double* q) -> double { if (LOCAL) return *q; return ld1_l2(q); };
   double w[KMAX];
-  const double rss = ld1_l2(F + fac_tail(mp)), icc = ld1_l2(F + fac_tail(mp) + 1);
+  const double rss = LD1(F + fac_tail(mp)), icc = LD1(F + fac_tail(mp) + 1);
   const double* z = F + fac_zoff(mp);
   *flags = 0;
   if (type == 1) {
@@ -332,22 +374,22 @@ BN_NOINLINE double score_move_stream(const double* C, int64_t ldc, const double*
       double a = ld_shared_ro(C + (int64_t)S[i] * ldc + j);
       int t = 0;
       for (; t + 1 < i; t += 2) {
-        const D2 l = ld2_l2(Li + t);
+        const D2 l = LD2(Li + t);
         a -= l.x * w[t];
         a -= l.y * w[t + 1];
       }
-      const D2 l = ld2_l2(Li + t);  // (L[i][i-1], 1/L[i][i]) or (1/L[i][i], pad)
+      const D2 l = LD2(Li + t);  // (L[i][i-1], 1/L[i][i]) or (1/L[i][i], pad)
       if (t < i) { a -= l.x * w[t]; a *= l.y; } else a *= l.x;
       w[i] = a;
       dj -= a * a;
-      ej -= a * ld1_l2(z + i);
+      ej -= a * LD1(z + i);
     }
     bool bad = !(rss == rss) || !(dj > 0.0);
     double rss_new = bad ? NAN : rss - ej * ej / dj;
     if (!bad && !(rss_new * icc > RSS_FLOOR)) { bad = true; rss_new = NAN; }
     if (rowout) {
       for (int t = 0; t < k; t++) rowout[t] = w[t];
-      rowout[row_tail(mp)] = dj; rowout[row_tail(mp) + 1] = ej; rowout[row_tail(mp) + 2] = rss_new;
+      rowout[row_tail(mp_row)] = dj; rowout[row_tail(mp_row) + 1] = ej; rowout[row_tail(mp_row) + 2] = rss_new;
     }
     if (bad) { *flags = SCORE_NPD; return -INFINITY; }
     return score_from_rss(rss_new, icc, k + 1, sc);
@@ -355,19 +397,26 @@ BN_NOINLINE double score_move_stream(const double* C, int64_t ldc, const double*
   if (!(rss == rss)) { *flags = SCORE_NOFACTOR; return 0.0; }
   double yy, yz;
   {
-    const double re = ld1_l2(F + fac_row(del) + del);
-    w[del] = re; yy = re * re; yz = re * ld1_l2(z + del);
+    const double re = LD1(F + fac_row(del) + del);
+    w[del] = re; yy = re * re; yz = re * LD1(z + del);
   }
   for (int i = del + 1; i < k; i++) {
     const double* Li = F + fac_row(i);
     double a = 0.0;
-    for (int t = del; t < i; t++) a -= ld1_l2(Li + t) * w[t];
-    a *= ld1_l2(Li + i);
+    for (int t = del; t < i; t++) a -= LD1(Li + t) * w[t];
+    a *= LD1(Li + i);
     w[i] = a;
     yy += a * a;
-    yz += a * ld1_l2(z + i);
+    yz += a * LD1(z + i);
   }
   return score_from_rss(rss + yz * yz / yy, icc, k - 1, sc);
+}
+
+template <int KMAX>
+BN_NOINLINE double score_move_stream(const double* C, int64_t ldc, const double* diag, int c, const int* S, int k,
+                                     int type, int j, int del, ScoreConsts sc, const double* F, int mp,
+                                     double* rowout, int* flags) {
+  return score_move_rows<KMAX, false>(C, ldc, diag, c, S, k, type, j, del, sc, F, mp, mp, rowout, flags);
 }
 
 // MaxPar <= 8: the whole block travels in registers (25 16-byte loads issued back to back: one
