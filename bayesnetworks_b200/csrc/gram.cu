@@ -22,6 +22,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "gram.h"
 
@@ -385,6 +391,112 @@ const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, doub
 // column sums, centres it in place and multiplies the tile pairs (i <= b, b).  Only the pairs of
 // the last block (2 / (n_tiles + 1) of the work) are left when the copy ends.  Every partial
 // tile is the same launch-independent computation, so the result has the bits of gram_build.
+// ---------------------------------------------------------------------------
+// Pageable host matrices (what R owns).  cudaMemcpyAsync from pageable memory is staged by the
+// driver through one thread (~8 GB/s); here a few host threads copy 8 MB chunks into a ring of
+// pinned buffers and every chunk goes to the device at the PCIe rate while the next one is being
+// staged.  Marshalling only: bytes are moved, nothing is computed on the host.
+// ---------------------------------------------------------------------------
+namespace {
+constexpr size_t STAGE_CHUNK = (size_t)8 << 20;
+constexpr int STAGE_BUFS = 4;
+constexpr int STAGE_THREADS = 4;
+
+class StagePool {
+ public:
+  static StagePool& get() { static StagePool p; return p; }
+  std::mutex use;  // one staged copy at a time
+  bool ready() {
+    if (state_ == 0) {
+      state_ = -1;
+      bool ok = true;
+      for (int b = 0; b < STAGE_BUFS && ok; b++) {
+        ok = cudaHostAlloc(&buf_[b], STAGE_CHUNK, cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&free_[b], cudaEventDisableTiming) == cudaSuccess;
+      }
+      if (ok) {
+        for (int t = 0; t < STAGE_THREADS; t++) workers_.emplace_back([this, t] { work(t); });
+        state_ = 1;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    return state_ == 1;
+  }
+  void* buffer(int b) { return buf_[b]; }
+  cudaEvent_t& event(int b) { return free_[b]; }
+  // dst[0..bytes) = src[0..bytes) by all workers; returns when done
+  void copy(void* dst, const void* src, size_t bytes) {
+    std::unique_lock<std::mutex> lk(mu_);
+    dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; pending_ = STAGE_THREADS; gen_++;
+    cv_.notify_all();
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  StagePool() {}
+  ~StagePool() {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      quit_ = true;
+      cv_.notify_all();
+    }
+    for (auto& w : workers_) w.join();
+  }
+  void work(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+      if (quit_) return;
+      seen = gen_;
+      const size_t per = (bytes_ / STAGE_THREADS + 63) & ~(size_t)63;
+      const size_t lo = per * t < bytes_ ? per * t : bytes_;
+      const size_t hi = lo + per < bytes_ ? lo + per : bytes_;
+      char* d = dst_; const char* s = src_;
+      lk.unlock();
+      if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  int state_ = 0;
+  void* buf_[STAGE_BUFS] = {};
+  cudaEvent_t free_[STAGE_BUFS] = {};
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  char* dst_ = nullptr; const char* src_ = nullptr;
+  size_t bytes_ = 0; int pending_ = 0; uint64_t gen_ = 0; bool quit_ = false;
+};
+
+bool host_is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+// columns [c0, c0 + nc) of the column-major host matrix -> device rows of stride ld_centered
+cudaError_t staged_block_copy(StagePool& sp, int& ring, const double* hX, int n_samples, int c0, int nc,
+                              double* dst, int64_t ld_centered, cudaStream_t copy_stream) {
+  const size_t col_bytes = (size_t)n_samples * 8;
+  int cols_per = (int)(STAGE_CHUNK / col_bytes);
+  if (cols_per < 1) return cudaErrorInvalidValue;  // (a single column above 8 MB: the caller uses the plain path)
+  for (int c = 0; c < nc; c += cols_per) {
+    const int n = (nc - c < cols_per) ? nc - c : cols_per;
+    const int b = ring++ % STAGE_BUFS;
+    cudaError_t e = cudaEventSynchronize(sp.event(b));  // the previous copy out of this buffer is done
+    if (e != cudaSuccess) return e;
+    sp.copy(sp.buffer(b), hX + (int64_t)(c0 + c) * n_samples, col_bytes * n);
+    e = cudaMemcpy2DAsync(dst + (int64_t)c * ld_centered, (size_t)ld_centered * 8, sp.buffer(b), col_bytes, col_bytes,
+                          (size_t)n, cudaMemcpyHostToDevice, copy_stream);
+    if (e != cudaSuccess) return e;
+    cudaEventRecord(sp.event(b), copy_stream);
+  }
+  return cudaSuccess;
+}
+}  // namespace
+
 const char* gram_build_from_host(const double* hX, int n_samples, int P, double* dXc, int64_t ld_centered,
                                  double* d_partial, const GramPlan& pl, double* d_colsum, double* d_mean,
                                  double* d_C, int64_t ldc, double* d_scratch_part, int* d_error_flag,
@@ -410,13 +522,26 @@ const char* gram_build_from_host(const double* hX, int n_samples, int P, double*
   if (chunks > GRAM_MEAN_MAX_CHUNKS) chunks = GRAM_MEAN_MAX_CHUNKS;
   int gx = (int)((ld_centered + 255) / 256);
   if (gx > 1024) gx = 1024;
+  // pageable source of some size: staged through pinned buffers by a few host threads
+  StagePool& sp = StagePool::get();
+  std::unique_lock<std::mutex> stage_lock(sp.use, std::defer_lock);
+  bool staged = (size_t)n_samples * P * 8 >= ((size_t)32 << 20) && (size_t)n_samples * 8 <= STAGE_CHUNK &&
+                host_is_pageable(hX);
+  if (staged) {
+    stage_lock.lock();
+    staged = sp.ready();
+    if (!staged) stage_lock.unlock();
+  }
+  int ring = 0;
   for (int b = 0; b < pl.n_tiles; b++) {
     const int c0 = b * TILE;
     const int nc = (P - c0 < TILE) ? P - c0 : TILE;
     double* dst = dXc + (int64_t)c0 * ld_centered;
     const double* src = hX + (int64_t)c0 * n_samples;
     cudaError_t e;
-    if (ld_centered == n_samples)
+    if (staged)
+      e = staged_block_copy(sp, ring, hX, n_samples, c0, nc, dst, ld_centered, copy_stream);
+    else if (ld_centered == n_samples)
       e = cudaMemcpyAsync(dst, src, (size_t)n_samples * nc * 8, cudaMemcpyHostToDevice, copy_stream);
     else
       e = cudaMemcpy2DAsync(dst, (size_t)ld_centered * 8, src, (size_t)n_samples * 8, (size_t)n_samples * 8,

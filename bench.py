@@ -14,6 +14,11 @@ A "step" is one whole job on that input: sufficient statistics (Gram) + all chai
           timed with CUDA events on the launching stream, max over ranks.
   e2e   : the same job through the host-pointer API (bn_create + bn_run): X starts in pinned
           host memory, H2D inside the timed region, traces copied back to the host.
+For N > 1 both timed regions contain the NCCL all-gather of the device-resident traces
+(`gather`); e2e then also shards the sample axis of X over the ranks (fixed-order exchange of
+partial statistics).  The line also carries `configs` (BASELINE configs 1, 2(i), 3 on one GPU and
+config 5 on eight, with parity flags), `strong_64_chains` (N > 1), `e2e.pageable_host` (N = 1)
+and `roofline.sm_cycles_per_iteration_per_chain`.
 One proposal scored = one iteration that reached checker() (src/network.h:330-336), i.e. one
 evaluation of a proposed parent set -- the definition under which the reference's
 iterations/s equals its proposals/s.
@@ -316,6 +321,17 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = timed(step_e2e, a.steps, max(1, a.warmup // 3))
 
+    # the same end-to-end step from PAGEABLE host memory (what R hands over): the driver stages the copy
+    pageable = None
+    if world == 1 and not a.no_configs:
+        Xp = np.array(Xh_np, order="F", copy=True)   # ordinary (pageable) allocation
+
+        def step_pageable():
+            with Context.from_data(Xp, g.source, g.target, nt, max_par=a.max_par, device=local_rank) as ctx:
+                ctx.run(n_chains=count, n_iter=a.iters, output=a.output, rng="wh", seeds=seeds)
+        pageable = timed(step_pageable, 2, 1) / 2
+        del Xp
+
     # per-step work (identical every step: same seeds)
     r0 = state["res"]
     (proposals, iters, alg_bytes, rows, nonpd), (chain_ms, gram_ms, cycles) = reduce_sum_max(
@@ -402,7 +418,10 @@ def run_ours(a):
                     "iters_per_sec": iters / (e2e_ms_per_step * 1e-3), "ms_per_step": e2e_ms_per_step,
                     "h2d_bytes_per_step": int(h2d_bytes + 4 * (2 * len(g.source) + a.nodes) + 12 * count),
                     "d2h_bytes_per_step": int((n_chains_total if world > 1 else count) * cap * 36 + 64 * count),
-                    "same_trajectories_as_resident_path": bool(same)},
+                    "same_trajectories_as_resident_path": bool(same),
+                    "pageable_host": (None if pageable is None else
+                                      {"ms_per_step": pageable, "value": proposals / (pageable * 1e-3), "unit": UNIT,
+                                       "note": "X in ordinary (pageable) host memory, as R owns it"})},
             "gpu_launches": int(r0["launches"]) * a.steps,
             "roofline": roofline,
             "step_breakdown_ms": {"gram_build": gram_ms, "chain_kernel": chain_ms},

@@ -239,3 +239,26 @@ def test_gpu_collinear_columns_are_flagged():
                 assert not ({3, 7} - {c}) & set(int(q) for q in r.final_parents[c, :r.final_npar[c]])
         base, score, hr = ctx.score_all_proposals(res[0].final_parents, res[0].final_npar)
         assert np.isfinite(base).all() and score[0, 3, 7] == -np.inf and score[0, 7, 3] == -np.inf
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_samples", [20000, 20001])
+def test_gpu_pageable_matrix_takes_the_staged_copy(n_samples):
+    """A pageable host matrix above 32 MB (what R hands over) is staged through pinned buffers by a few
+    host threads (gram.cu: StagePool); same statistics as the one-shot paths, ragged sample counts too."""
+    import torch
+    from bayesnetworks_b200 import Context
+    rng = np.random.default_rng(3)
+    P = 300
+    X = np.asfortranarray(rng.standard_normal((n_samples, P)) + rng.uniform(-2, 2, P))   # 48 MB, pageable
+    nt = np.zeros(P, np.int32)
+    with Context.from_data(X, [1], [2], nt, max_par=4) as a:
+        sa = a.stats()
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    with Context.from_device(Xd.data_ptr(), n_samples, n_samples, P, [1], [2], nt, max_par=4) as b:
+        sb = b.stats()
+    for x, y in zip(sa, sb):
+        assert np.array_equal(x, y)          # same bits as the device-resident build
+    mean = X.mean(axis=0)
+    Xc = X - mean
+    np.testing.assert_allclose(sa[3], Xc.T @ Xc, rtol=1e-11, atol=1e-7)
