@@ -723,6 +723,23 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   ChainWorkspace w;
   memset(&w, 0, sizeof(w));
   w.scratch_n = scratch_words((int)P, HELPER_WARPS + 1, 32);
+  {
+    // Two CTAs per chain (chain_pipe_kernel) when every chain can have its SM pair at once: MaxPar <= 8,
+    // the whole state fits in shared memory, 2 * n_chains <= SMs.  Opt-in for now: BN_B200_PIPE=1
+    // (A/B runs, tests that compare the two forms).
+    const char* e = getenv("BN_B200_PIPE");
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    ChainParams q;
+    memset(&q, 0, sizeof(q));
+    q.P = (int)P; q.max_par = (int)MP; q.W = (int)W;
+    // (its team operations are dealt over the seven helper warps: larger row lists per part)
+    const int sn = scratch_words((int)P, HELPER_WARPS, 32) > w.scratch_n ? scratch_words((int)P, HELPER_WARPS, 32) : w.scratch_n;
+    w.pipeline = (e && e[0] != '0' && MP <= 8 && 2 * nc <= n_sm && chains_can_pipeline(q, sn)) ? 1 : 0;
+    if (w.pipeline) w.scratch_n = sn;
+    if (w.pipeline && e && e[0] == '3') w.pipeline = 3;  // (developer switch: the chain's CTA rebuilds every window itself)
+  }
+  const size_t dscore_n = (size_t)(nc * P * MP) * (w.pipeline ? 2 : 1);
   CU_TRY(buf.alloc(&w.par, (size_t)(nc * P * MP)));
   CU_TRY(buf.alloc(&w.born, (size_t)(nc * P * MP)));
   CU_TRY(buf.alloc(&w.npar, (size_t)(nc * P)));
@@ -731,12 +748,12 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   CU_TRY(buf.alloc(&w.haspar, (size_t)(nc * W)));
   CU_TRY(buf.alloc(&w.hp_list, (size_t)(nc * P)));
   CU_TRY(buf.alloc(&w.scratch, (size_t)nc * w.scratch_n));
-  CU_TRY(buf.alloc(&w.dscore, (size_t)(nc * P * MP)));
+  CU_TRY(buf.alloc(&w.dscore, dscore_n));
   if (MP > 8) {  // per-node Cholesky factors + the candidate rows of a round (score_core.cuh)
     CU_TRY(buf.alloc(&w.fac, (size_t)(nc * P * fac_stride(fac_mp((int)MP)))));
     CU_TRY(buf.alloc(&w.rowbuf, (size_t)nc * REPLAY_POS * row_stride(fac_mp((int)MP))));
   }
-  CU_TRY(cudaMemsetAsync(w.dscore, 0xff, (size_t)(nc * P * MP) * sizeof(double), c->stream));  // NaN = unknown
+  CU_TRY(cudaMemsetAsync(w.dscore, 0xff, dscore_n * sizeof(double), c->stream));  // NaN = unknown (tags: -1)
   const bool dev_out = a->device_outputs != 0;
   if (dev_out) {
     w.t_iter = trace->iter; w.t_changed = trace->changed_node; w.t_movetype = trace->movetype;
@@ -812,9 +829,11 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
       }
     }
     int* d_pos = nullptr;
-    CU_TRY(buf.alloc(&ra.mt_states, mt.size()));
+    CU_TRY(buf.alloc(&ra.mt_states, mt.size() * (w.pipeline ? 2 : 1)));
     CU_TRY(buf.alloc(&d_pos, (size_t)nc));
     CU_TRY(cudaMemcpyAsync(ra.mt_states, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    if (w.pipeline)  // the record builder's own copy of the stream state
+      CU_TRY(cudaMemcpyAsync(ra.mt_states + mt.size(), mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaMemcpyAsync(d_pos, mt_pos.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, c->stream));
     ra.mt_pos = d_pos;
   }
@@ -856,6 +875,12 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
   std::vector<ChainResult> res(nc);
   CU_TRY(cudaMemcpy(res.data(), d_res, sizeof(ChainResult) * nc, cudaMemcpyDeviceToHost));
   int rc = BN_OK;
+  if (w.pipeline && getenv("BN_B200_PIPE_STATS"))
+    for (int ch = 0; ch < nc && ch < 4; ch++)
+      fprintf(stderr, "[bn_b200] chain %d two-CTA: %d windows requested, %d waits for the builder, %d discarded, %d in-place rebuilds, %lld cycles\n",
+              ch, res[ch].pipe[0], res[ch].pipe[1], res[ch].pipe[2], res[ch].pipe[3], (long long)res[ch].cyc_total),
+      fprintf(stderr, "[bn_b200]   cycles: wait %lld, copy %lld, batch repair %lld, redo after it %lld, stale rebuilds %lld, publish %lld\n",
+              res[ch].pipe_cyc[0], res[ch].pipe_cyc[1], res[ch].pipe_cyc[2], res[ch].pipe_cyc[3], res[ch].pipe_cyc[4], res[ch].pipe_cyc[5]);
   std::vector<int> nrows(nc), nmoves(nc);
   for (int ch = 0; ch < nc; ch++) {
     nrows[ch] = res[ch].n_rows;

@@ -81,6 +81,8 @@ struct ChainParams {  // read-only, shared by all chains of a run
   int g_chunks, g_lpr, g_rpp;
 };
 
+struct PipeLink;
+
 struct ChainMem {  // per-chain global memory
   int* par;            // [P][max_par] ordered parent lists (edges[child])
   int* npar;           // [P]
@@ -101,6 +103,12 @@ struct ChainMem {  // per-chain global memory
   double* dscore;      // [P][max_par] cache of score(c | parents without slot e), NaN = unknown; or null
   int* npar_freq;      // [P][max_par + 1] iterations node p spent with k parents, or null
   int* npar_since;     // [P] first counted iteration of the node's current parent count
+  // two-CTA pipeline (chain_pipe_kernel; device only, null otherwise)
+  uint32_t* nver = nullptr;   // [P] accepted moves per node: the tag of the node's dscore entries -- with it
+                              // dscore is [P][max_par] PAIRS (score, tag) and nothing is ever invalidated
+  PipeLink* pipe = nullptr;        // mailbox shared with the peer CTA of the cluster
+  int pipe_rank = 0;          // 0 = the chain's CTA, 1 = the record builder
+  int pipe_debug = 0;         // (developer switch BN_B200_PIPE=3) 1: every window is rebuilt by the chain's own CTA
 };
 
 struct ChainScalars {  // lives in registers (warp-uniform)
@@ -128,6 +136,13 @@ struct ChainScalars {  // lives in registers (warp-uniform)
   int anc_changed;     // the last accepted move changed ancestor rows (else no cycle bit can differ)
   int next_log;        // smallest multiple of output_every >= s.iter (rounds; n_iter is an int)
   int status;
+  // two-CTA pipeline (chain's CTA): first stream position of the window in ws (-1: none), the
+  // outstanding request (number, position, in flight?), counters
+  int64_t pw_cur, pw_out_pos;
+  int pw_out_seq, pw_out;
+  int pw_seen;         // accepted moves the records in ws have been repaired for
+  int pw_waits, pw_discards, pw_rebuilds;
+  long long pw_cyc[6];  // (diagnostics build) wait for the builder, copy, batch repair, redo after it, stale rebuilds, publish
 };
 
 struct WindowSlots {  // shared memory on the device
@@ -380,7 +395,7 @@ BN_HD void anc_add_part(const ChainParams& p, const ChainMem& m, int j, int c, i
 // equal share of the rows of an ancestor update (the scan and the ORs are independent per row).
 constexpr int HELPER_WARPS = 7;
 enum { HELPER_EXIT = 0, HELPER_ANC_ADD = 1, HELPER_RECORDS = 2, HELPER_REPAIR = 3, HELPER_ANC_DEL = 4,
-       HELPER_FILL_WH = 5 };
+       HELPER_FILL_WH = 5, HELPER_PIPE_COPY = 6, HELPER_REPAIR_BATCH = 7 };
 // command block (ints): [0] op, [1..2] stream position, [3..4] ring limit, [5] n_haspar,
 // [6] TotalEdges, [7] Nagree, [8] node / parent, [9] child, [10] span limit (atomicMin target),
 // [11] child dropped below MaxPar
@@ -390,6 +405,108 @@ __device__ __forceinline__ void cta_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"((HELPER_WARPS + 1) * 32) : "memory");
 }
 #endif
+// ---------------------------------------------------------------------------
+// Two-CTA pipeline (chain_pipe_kernel in kernels.cu; MaxPar <= 8 with the whole state in shared
+// memory).  A chain is a thread-block CLUSTER of two CTAs on two SMs:
+//   rank 0  the chain: walks the records, commits, applies the accepted moves -- everything the
+//           single-CTA kernel does except building the records of a window;
+//   rank 1  the record builder: keeps a REPLICA of the graph state (parent lists, ancestor
+//           bitsets, scores, its own copy of the uniform stream) by applying the accepted moves
+//           the chain publishes, and builds the 256 position records of the NEXT window while the
+//           chain is busy with the current one.
+// A window is picked up by copying its records over distributed shared memory; it was built when
+// the replica had applied a known number of moves, so the chain repairs it for the moves accepted since
+// (repair_record_batch: the same rules as the in-round repair, applied for a list of moves), and
+// from there on everything is the single-CTA round.  Windows sit on a 256-position grid; a stale
+// record under the walk is rebuilt in place by the chain's own CTA.
+// Mailboxes: each CTA polls its OWN shared memory; the peer writes into it with remote stores
+// (mapa + st.shared::cluster).
+// ---------------------------------------------------------------------------
+constexpr int PIPE_WIN = HELPER_WARPS * 32;  // stream positions per window: one record per HELPER thread.  In this
+                               // form the chain warps only direct (walk, commit, mailbox): every team operation is
+                               // executed by the seven helper warps alone, so each SM runs ONE copy of its code
+                               // (the one-CTA kernel keeps a second, inlined copy for warp 0 -- the instruction
+                               // cache is what limits these kernels)
+constexpr int PIPE_MQ = 64;    // accepted moves in flight between the two CTAs (back-pressure beyond)
+constexpr int PIPE_LOG = 128;  // recent moves the chain remembers for the windows it picks up
+// Every message is ONE store of at most 16 bytes that carries its own sequence number, so no message
+// needs a second store to become valid and nothing depends on the order in which remote stores land
+// (st.release.cluster compiles to MEMBAR.ALL.GPU on sm_100a: ~1,000 cycles per accepted move).
+struct PipeLink {
+  // written by the chain's CTA into the BUILDER's copy
+  unsigned long long req;      // window request: (first stream position << 16) | (request number & 0xffff)
+  int req_exit;
+  int pad0;
+  // written by the builder into the CHAIN's copy
+  unsigned long long rdy;      // window completed: (moves the replica had applied << 32) | its request number
+  int mq_tail;                 // moves the builder has taken out of the queue
+  int pad1;
+  // accepted moves (builder's copy): [0] move number + 1, [1] child | parent << 11 | (type - 1) << 22 |
+  // deletion slot << 23 | in-prior << 26 | (move number + 1) << 27, [2..3] the child's new score
+  alignas(16) int mq[PIPE_MQ][4];
+  int log[PIPE_LOG];           // (chain's copy) node | dropped below MaxPar << 24 | ancestor rows changed << 25 |
+                               // set of nodes with parents changed << 26
+};
+constexpr int PIPE_MAX_NODES = 2048;  // 11-bit node numbers in a move message
+constexpr int LOG_NODE = 0xffffff, LOG_UNFULL = 1 << 24, LOG_ANC = 1 << 25, LOG_HP = 1 << 26;
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t peer_addr(const void* p, int rank) {  // the same variable in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_peer(uint32_t a, int v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_peer64(uint32_t a, unsigned long long v) {
+  asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_peer128(uint32_t a, int x, int y, int z, int w) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// polls of this CTA's own mailbox (the peer writes it remotely)
+__device__ __forceinline__ int ld_poll(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.cluster.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_poll64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ld_poll128(const int* p, int& x, int& y, int& z, int& w) {
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(smem_addr(p)) : "memory");
+}
+__device__ __forceinline__ int ld_peer(uint32_t a) {
+  int v;
+  asm volatile("ld.shared::cluster.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_peer64(uint32_t a) {
+  long long v;
+  asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// chain's CTA, lane 0: hand accepted move number `n` to the builder and remember it locally
+__device__ __forceinline__ void pipe_publish(const ChainMem& m, int n, int type, int c, int j, int del, int ag,
+                                             double score, int flags) {
+  PipeLink* lk = m.pipe;
+  while (n - ld_poll(&lk->mq_tail) >= PIPE_MQ) {}
+  const long long sb = __double_as_longlong(score);
+  st_peer128(peer_addr(&lk->mq[n % PIPE_MQ][0], 1), n + 1,
+             c | (j << 11) | ((type - 1) << 22) | (del << 23) | (ag << 26) | ((n + 1) << 27),
+             (int)(sb & 0xffffffffll), (int)(sb >> 32));
+  lk->log[n % PIPE_LOG] = c | flags;
+}
+#endif
+
 // barrier between the rounds of a team operation (all warps of the CTA, or just this warp)
 BN_HD void team_sync(const ChainMem& m) {
 #if defined(__CUDA_ARCH__)
@@ -418,7 +535,7 @@ BN_HD void anc_after_add(const ChainParams& p, ChainMem& m, int j, int c, int& m
     if (Warp::lane() == 0) { m.helper[8] = j; m.helper[9] = c; m.helper[0] = HELPER_ANC_ADD; }
     Warp::sync();
     cta_bar(1);
-    anc_add_part(p, m, j, c, m.scratch, 0, HELPER_WARPS + 1);
+    if (!m.pipe) anc_add_part(p, m, j, c, m.scratch, 0, HELPER_WARPS + 1);  // (two-CTA form: the helper warps own all rows)
     cta_bar(2);
     return;
   }
@@ -473,10 +590,11 @@ BN_HD DelLayout del_layout(const ChainParams& p, const ChainMem& m, int nparts) 
 BN_HD int anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part, int nparts, long long* dbg = nullptr) {
   const int l = Warp::lane(), W = p.W, MP = p.max_par;
   const DelLayout lay = del_layout(p, m, nparts);
-  int* list = lay.lists + part * 2 * lay.per;
+  int* list = lay.lists + (part < 0 ? 0 : part) * 2 * lay.per;
   int* list2 = list + lay.per;
   const long long td0 = cycle_now();
-  const int n = collect_desc_part(p, m, c, 0, list, part, nparts);  // old column c: rows this warp owns
+  // (part < 0, two-CTA form: the chain's warp has no rows of its own -- it keeps the round barriers and the bookkeeping)
+  const int n = part < 0 ? 0 : collect_desc_part(p, m, c, 0, list, part, nparts);  // old column c: rows this warp owns
   BN_STAT(emu_stats().del_desc += n;)
   const uint32_t lt = (l == 31) ? 0x7fffffffu : ((1u << l) - 1u);
   // L is usually confined to one or two 128-bit chunks: a lane takes one (row, non-zero chunk)
@@ -506,7 +624,7 @@ BN_HD int anc_del_team(const ChainParams& p, const ChainMem& m, int c, int part,
     const long long tr0 = cycle_now();
     const uint32_t* dprev = lay.dirty + (round % 3) * W;
     uint32_t* dnext = lay.dirty + ((round + 1) % 3) * W;
-    if (part == 0) {  // nobody reads or writes these during this round
+    if (part <= 0 && (part < 0 || !m.pipe)) {  // nobody reads or writes these during this round
       uint32_t* dclr = lay.dirty + ((round + 2) % 3) * W;
       for (int w = l; w < W; w += Warp::NL) dclr[w] = 0u;
       if (l == 0) lay.flags[(round + 2) % 4] = 0;
@@ -595,7 +713,7 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc
   const int l = Warp::lane();
   int nparts = 1;
 #if defined(__CUDA_ARCH__)
-  if (m.helper) nparts = HELPER_WARPS + 1;
+  if (m.helper) nparts = m.pipe ? HELPER_WARPS : HELPER_WARPS + 1;
 #endif
   const DelLayout lay = del_layout(p, m, nparts);
   {
@@ -641,7 +759,7 @@ BN_HD void anc_after_delete(const ChainParams& p, ChainMem& m, int c, int& m_anc
     if (l == 0) { m.helper[9] = c; m.helper[0] = HELPER_ANC_DEL; }
     Warp::sync();
     cta_bar(1);
-    anc_del_team(p, m, c, 0, nparts, dbg);
+    anc_del_team(p, m, c, m.pipe ? -1 : 0, nparts, dbg);
     cta_bar(2);
     return;
   }
@@ -751,12 +869,14 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStr
     // unused slots hold -1 (load_par8 relies on it)
     const int c = (int)(i / MP), e = (int)(i % MP);
     m.par[i] = (p.initial_network == 0 && e < p.prior_npar[c]) ? p.prior_par[(int64_t)c * p.prior_stride + e] : -1;
-    m.born[i] = p.drop;  // edges of the start graph are counted from iteration `drop`
+    if (m.born) m.born[i] = p.drop;  // edges of the start graph are counted from iteration `drop`
   }
   if (m.npar_freq)
     for (int i = l; i < P; i += Warp::NL) m.npar_since[i] = p.drop;
   for (int i = l; i < P; i += Warp::NL) m.npar[i] = (p.initial_network == 0) ? p.prior_npar[i] : 0;
   for (int w = l; w < p.W; w += Warp::NL) m.haspar[w] = 0u;
+  if (m.nver)
+    for (int i = l; i < P; i += Warp::NL) m.nver[i] = 0u;
   Warp::sync();
   int64_t start_pos = 0;
   if (p.initial_network == 1) {
@@ -804,6 +924,8 @@ BN_HD void chain_init(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStr
   s.n_rows = 0; s.n_moves = 0; s.valid_iters = 0; s.alg_bytes = 0;
   s.gll_ok = 0; s.gll = 0.0;
   s.win = 4; s.windows = 0; s.status = 0; s.need_full = 0; s.anc_changed = 0; s.next_log = 0;
+  s.pw_cur = -1; s.pw_seen = 0; s.pw_out_pos = 0; s.pw_out_seq = 0; s.pw_out = 0; s.pw_waits = 0; s.pw_discards = 0; s.pw_rebuilds = 0;
+  for (int t = 0; t < 6; t++) s.pw_cyc[t] = 0;
   for (int t = 0; t < 12; t++) s.cyc[t] = 0;
   s.slots_sim = 0;
 }
@@ -1029,7 +1151,8 @@ BN_HD void phase_bc(const ChainParams& p, const ChainMem& m, const ChainScalars&
 struct RoundCtx {  // warp-uniform, handed to the helper warps through the command block
   int64_t pos, hi;
   int n_haspar, te_true, agree_true;
-  int redo_from;  // -1: build every record; >= 0: rebuild the deletion records from this slot on
+  int redo_from;  // -1: build every record; >= 0: rebuild records from this slot on, namely ...
+  int redo_mode;  // ... 0: the deletion records; 1: the stale records; 2: all of them
 };
 
 // draw replay of the iteration that would start at stream position q -> record `slot`
@@ -1287,7 +1410,9 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
     // the set of nodes with parents changed: deletion draws index into it (src/network.h:311-319),
     // so the deletion records behind the walk are replayed and decided again; additions keep theirs
     const int old = ws.t_rec[slot];
-    if (slot < rc.redo_from || !(old & REC_TYPE) || (old & REC_OVF)) active = false;
+    if (slot < rc.redo_from) active = false;
+    else if (rc.redo_mode == 0) active = (old & REC_TYPE) && !(old & REC_OVF);
+    else if (rc.redo_mode == 1) active = (old & REC_STALE) != 0;
   }
 #if defined(__CUDA_ARCH__)
   if constexpr (KMAX > 8) {
@@ -1317,7 +1442,21 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
   // logarithm of the acceptance uniform is taken while they are in flight.
   const int rc_c = ws.t_c[slot], rc_j = ws.t_j[slot];
   double* cache = (m.dscore && (rec & REC_TYPE)) ? m.dscore + (uint32_t)rc_c * (uint32_t)p.max_par + ws.t_e[slot] : nullptr;
-  const double cached = cache ? ld_shared_ro(cache) : nan_sentinel();
+  double cached = nan_sentinel();
+#if defined(__CUDA_ARCH__)
+  // two-CTA pipeline: the table holds (score, tag) pairs, tag = the number of accepted moves at the
+  // child when the score was computed.  The chain's CTA and the record builder lag each other by a
+  // few moves; an entry is valid for whoever holds the same count, and nothing is ever invalidated
+  // (a late store of an outdated score carries an outdated tag).
+  long long tag = 0;
+  if (m.nver && cache) {
+    cache += (cache - m.dscore);  // pairs
+    tag = (long long)m.nver[rc_c];
+    const D2 v = ld2_l2(cache);
+    if (__double_as_longlong(v.y) == tag) cached = v.x;
+  } else
+#endif
+  if (cache) cached = ld_shared_ro(cache);
   const int ag = ld_shared_ro(p.sim_edge + (int64_t)rc_j + (int64_t)rc_c * p.P) ? REC_AG : 0;
   ws.t_lu[slot] = log(ubuf[(rc.pos + slot + (rec & REC_LEN_MASK)) & (RNG_CAP - 1)]);
   if (cached == cached) {
@@ -1328,6 +1467,12 @@ BN_HD void build_record(const ChainParams& p, const ChainMem& m, const RoundCtx&
     sc = score_proposal<KMAX>(p, m, (rec & REC_TYPE) ? 2 : 1, ws.t_c[slot], ws.t_j[slot], ws.t_e[slot],
                               KMAX > 8 ? m.rowbuf + (uint32_t)slot * (uint32_t)row_stride(fac_mp(p.max_par)) : nullptr,
                               &kk, &npd);
+#if defined(__CUDA_ARCH__)
+    if (m.nver && cache) {
+      D2 w; w.x = sc; w.y = __longlong_as_double(tag);
+      *(D2*)cache = w;
+    } else
+#endif
     if (cache) *cache = sc;  // (duplicates within a round store the same value)
   }
   ws.t_score[slot] = sc;
@@ -1368,12 +1513,64 @@ BN_HD void repair_record(const ChainParams& p, const ChainMem& m, WindowSlots& w
 }
 
 #if defined(__CUDACC__)
+// Two-CTA pipeline: a window built when the replica had applied `lo` moves is repaired for the moves
+// lo .. hi-1 the chain has accepted since -- repair_record's rules for every move of the list, the
+// cycle bit re-tested once against the current ancestor rows (`retest`: one of the moves changed them).
+__device__ __forceinline__ void repair_record_batch(const ChainParams& p, const ChainMem& m, WindowSlots& ws, int slot,
+                                                    int from, int lo, int hi, int retest) {
+  if (slot < from) return;
+  int rec = ws.t_rec[slot];
+  if (rec & (REC_OVF | REC_STALE)) return;
+  const int rc_c = ws.t_c[slot];
+  const bool add = !(rec & REC_TYPE);
+  const uint32_t f = ws.t_full[slot];
+  bool stale = (rec & REC_CLOSE) != 0;
+  for (int i = lo; i < hi; i++) {
+    const int e = m.pipe->log[i % PIPE_LOG];
+    const int c = e & LOG_NODE;
+    stale |= (c == rc_c);
+    if ((e & LOG_UNFULL) && add) {
+      const uint32_t cc = (uint32_t)(c + 1);
+      stale |= (rec & REC_FULLMANY) || (f & 0xffffu) == cc || (f >> 16) == cc;
+    }
+  }
+  if (!stale && retest && add) {
+    const int cyc = test_bit(m.anc + (int64_t)ws.t_j[slot] * p.Ws, rc_c) ? 1 : 0;
+    if (cyc != ((rec & REC_CYC) ? 1 : 0)) {
+      if (!cyc && (rec & REC_NOSCORE)) {
+        stale = true;  // it was never scored
+      } else {
+        rec = (rec & ~REC_CYC) | (cyc ? REC_CYC : 0);
+        ws.t_rec[slot] = rec;
+        ws.t_walk[slot] = walk_word(rec);
+      }
+    }
+  }
+  if (stale) {
+    ws.t_rec[slot] = rec | REC_STALE;
+    ws.t_walk[slot] = WALK_STALE;
+  }
+}
+
+// record `slot` of the window the builder (rank 1) holds -> this CTA's copy, over distributed shared memory
+__device__ __forceinline__ void pipe_copy_record(WindowSlots& ws, int slot) {
+  const int c = ld_peer(peer_addr(&ws.t_c[slot], 1)), j = ld_peer(peer_addr(&ws.t_j[slot], 1));
+  const int e = ld_peer(peer_addr(&ws.t_e[slot], 1)), rec = ld_peer(peer_addr(&ws.t_rec[slot], 1));
+  const int full = ld_peer(peer_addr(&ws.t_full[slot], 1)), walk = ld_peer(peer_addr(&ws.t_walk[slot], 1));
+  const long long sc = ld_peer64(peer_addr(&ws.t_score[slot], 1)), lu = ld_peer64(peer_addr(&ws.t_lu[slot], 1));
+  ws.t_c[slot] = c; ws.t_j[slot] = j; ws.t_e[slot] = e; ws.t_rec[slot] = rec;
+  ws.t_full[slot] = (uint32_t)full; ws.t_walk[slot] = walk;
+  ws.t_score[slot] = __longlong_as_double(sc); ws.t_lu[slot] = __longlong_as_double(lu);
+}
+#endif
+
+#if defined(__CUDACC__)
 __device__ __forceinline__ void helper_post(const ChainMem& m, int op, const RoundCtx& rc) {
   if (Warp::lane() == 0) {
     m.helper[1] = (int)(rc.pos & 0xffffffffll); m.helper[2] = (int)(rc.pos >> 32);
     m.helper[3] = (int)(rc.hi & 0xffffffffll); m.helper[4] = (int)(rc.hi >> 32);
     m.helper[5] = rc.n_haspar; m.helper[6] = rc.te_true; m.helper[7] = rc.agree_true;
-    m.helper[8] = rc.redo_from;
+    m.helper[8] = rc.redo_from; m.helper[11] = rc.redo_mode;
     m.helper[0] = op;
   }
   Warp::sync();
@@ -1383,7 +1580,7 @@ __device__ __forceinline__ RoundCtx helper_ctx(const ChainMem& m) {
   rc.pos = ((int64_t)m.helper[2] << 32) | (uint32_t)m.helper[1];
   rc.hi = ((int64_t)m.helper[4] << 32) | (uint32_t)m.helper[3];
   rc.n_haspar = m.helper[5]; rc.te_true = m.helper[6]; rc.agree_true = m.helper[7];
-  rc.redo_from = m.helper[8];
+  rc.redo_from = m.helper[8]; rc.redo_mode = m.helper[11];
   return rc;
 }
 
@@ -1426,7 +1623,9 @@ __device__ __forceinline__ void team_fill_wh(const ChainMem& m, RngStream& r, in
 }
 
 // body of a helper warp (warp index 1..HELPER_WARPS of the chain's CTA)
-template <int KMAX>
+// PIPE (two-CTA form): the helper warps do ALL the work of a team operation -- slots and row blocks
+// are dealt over HELPER_WARPS parts
+template <int KMAX, bool PIPE = false>
 __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem& m, int part,
                                             double* ubuf, WindowSlots& ws) {
   const WhJump jump = wh_jump_for_thread();
@@ -1434,32 +1633,41 @@ __device__ __forceinline__ void helper_loop(const ChainParams& p, const ChainMem
     cta_bar(1);
     const int op = m.helper[0];
     if (op == HELPER_EXIT) break;
-    const int slot = part * 32 + Warp::lane();
+    const int slot = (PIPE ? part - 1 : part) * 32 + Warp::lane();
     if (op == HELPER_RECORDS) {
       build_record<KMAX>(p, m, helper_ctx(m), ubuf, ws, slot);
     } else if (op == HELPER_REPAIR) {
       repair_record(p, m, ws, slot, m.helper[9], m.helper[11], m.helper[7], m.helper[8]);
     } else if (op == HELPER_ANC_ADD) {
-      anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * rows_per_part(p.P, HELPER_WARPS + 1, Warp::NL), part,
-                   HELPER_WARPS + 1);
+      if (PIPE)
+        anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + (part - 1) * rows_per_part(p.P, HELPER_WARPS, Warp::NL), part - 1,
+                     HELPER_WARPS);
+      else
+        anc_add_part(p, m, m.helper[8], m.helper[9], m.scratch + part * rows_per_part(p.P, HELPER_WARPS + 1, Warp::NL), part,
+                     HELPER_WARPS + 1);
     } else if (op == HELPER_ANC_DEL) {
-      anc_del_team(p, m, m.helper[9], part, HELPER_WARPS + 1);
+      if (PIPE) anc_del_team(p, m, m.helper[9], part - 1, HELPER_WARPS);
+      else anc_del_team(p, m, m.helper[9], part, HELPER_WARPS + 1);
     } else if (op == HELPER_FILL_WH) {
       fill_wh_thread(m, ubuf, jump);
+    } else if (op == HELPER_PIPE_COPY) {
+      pipe_copy_record(ws, slot);
+    } else if (op == HELPER_REPAIR_BATCH) {
+      repair_record_batch(p, m, ws, slot, m.helper[8], m.helper[5], m.helper[6], m.helper[7]);
     }
     cta_bar(2);
   }
 }
 #endif
 
-template <int KMAX>
+template <int KMAX, bool PIPE = false>
 BN_HD void team_records(const ChainParams& p, const ChainMem& m, const RoundCtx& rc, const double* ubuf,
                         WindowSlots& ws) {
 #if defined(__CUDA_ARCH__)
   if (m.helper) {
     helper_post(m, HELPER_RECORDS, rc);
     cta_bar(1);
-    build_record<KMAX>(p, m, rc, ubuf, ws, Warp::lane());
+    if constexpr (!PIPE) build_record<KMAX>(p, m, rc, ubuf, ws, Warp::lane());
     cta_bar(2);
     return;
   }
@@ -1480,7 +1688,7 @@ BN_HD void team_repair(const ChainParams& p, const ChainMem& m, WindowSlots& ws,
     }
     Warp::sync();
     cta_bar(1);
-    repair_record(p, m, ws, Warp::lane(), c, unfull, retest, from);
+    if (!m.pipe) repair_record(p, m, ws, Warp::lane(), c, unfull, retest, from);
     cta_bar(2);
   }
 #else
@@ -1523,7 +1731,7 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
                            int j, int del, double new_score, int ag, const double* newrow) {
   const int MP = p.max_par, l = Warp::lane();
   int* pc = m.par + (int64_t)c * MP;
-  int* bc = m.born + (int64_t)c * MP;
+  int* bc = m.born ? m.born + (int64_t)c * MP : nullptr;  // (only read with edge_freq)
   const int k = m.npar[c];
   double* F = KMAX > 8 ? m.fac + (int64_t)c * fac_stride(fac_mp(MP)) : nullptr;
 #if defined(__CUDA_ARCH__)
@@ -1540,6 +1748,15 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
 #endif
   const long long tq0 = cycle_now();
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
+#if defined(__CUDA_ARCH__)
+  // two-CTA pipeline: the builder's replica starts on the move while this CTA applies it
+  const bool publish = m.pipe && m.pipe_rank == 0;
+  const long long tp0 = cycle_now();
+  if (publish && l == 0)
+    pipe_publish(m, s.n_moves, type, c, j, type == 2 ? del : 0, ag, new_score,
+                 ((type == 2 && k == MP) ? LOG_UNFULL : 0) | ((type == 1 ? k == 0 : k == 1) ? LOG_HP : 0));
+  s.pw_cyc[5] += cycle_now() - tp0;
+#endif
   Warp::sync();
   if (l == 0 && m.npar_freq) {
     // freqNpar[p][Npar[p]]++ of Tabulate() (Bayes-networks/main.cpp:291): the old count held
@@ -1619,10 +1836,15 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
     F[fac_zoff(mp) + k] = newrow[row_tail(mp) + 1] * r; F[fac_tail(mp)] = newrow[row_tail(mp) + 2];
 #endif
   }
-  if (m.dscore) {  // the deletion scores of c are no longer valid
+  if (m.nver) {  // the deletion scores of c carry the old count: no longer valid
+    if (l == 0) m.nver[c]++;
+  } else if (m.dscore) {  // the deletion scores of c are no longer valid
     double* dc = m.dscore + (uint32_t)c * (uint32_t)MP;
     for (int e = l; e < MP; e += Warp::NL) dc[e] = nan_sentinel();
   }
+#if defined(__CUDA_ARCH__)
+  if (publish && l == 0 && s.anc_changed) m.pipe->log[s.n_moves % PIPE_LOG] |= LOG_ANC;
+#endif
   if (s.n_moves < p.moves_capacity) {
     if (l == 0) {
       int* mv = m.moves + (int64_t)s.n_moves * 4;
@@ -1815,7 +2037,7 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   RoundCtx rc;
   rc.pos = s.read_pos; rc.hi = rng.gen_hi;
   rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
-  rc.redo_from = -1;
+  rc.redo_from = -1; rc.redo_mode = 0;
   while (s.next_log < (int)s.iter) s.next_log += p.output_every;  // (after sequential windows; else no step)
   team_records<KMAX>(p, m, rc, rng.ubuf, ws);
   long long t1 = cycle_now();
@@ -1850,7 +2072,7 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
       if (s.n_haspar != nh0) {
         // the set of nodes with parents changed: the deletion records behind the walk are redone
         rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
-        rc.redo_from = k;
+        rc.redo_from = k; rc.redo_mode = 0;
         team_records<KMAX>(p, m, rc, rng.ubuf, ws);
       }
       s.cyc[2] += cycle_now() - t0;
@@ -1858,15 +2080,209 @@ BN_HD void run_round(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   }
 }
 
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------
+// Two-CTA pipeline, chain side (rank 0; see PipeLink).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pipe_request(const ChainMem& m, ChainScalars& s, int64_t pos) {
+  s.pw_out_seq++; s.pw_out = 1; s.pw_out_pos = pos;
+  if (Warp::lane() == 0)
+    st_peer64(peer_addr(&m.pipe->req, 1), ((unsigned long long)pos << 16) | (unsigned long long)(s.pw_out_seq & 0xffff));
+}
+
+// make ws hold the window that contains s.read_pos: the one the builder was asked for ahead of time
+// if the walk arrived there, else a fresh request; then repair it for the moves it has not seen
+// (returns the number of moves the builder's replica had applied when it built the window)
+template <int KMAX>
+__device__ __forceinline__ int pipe_acquire(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
+                                            WindowSlots& ws) {
+  PipeLink* lk = m.pipe;
+  const int l = Warp::lane();
+  const int64_t want = (s.pw_cur >= 0 && s.read_pos >= s.pw_cur + PIPE_WIN && s.read_pos < s.pw_cur + 2 * PIPE_WIN)
+                           ? s.pw_cur + PIPE_WIN : s.read_pos;
+  const long long ta0 = cycle_now();
+  int applied = 0;
+  for (;;) {
+    if (!s.pw_out) pipe_request(m, s, want);
+    unsigned long long rdy = 0ull;
+    if (l == 0) {
+      int spins = 0;
+      while ((int)((rdy = ld_poll64(&lk->rdy)) & 0xffffull) != (s.pw_out_seq & 0xffff)) spins = 1;
+      s.pw_waits += spins;
+    }
+    applied = Warp::shfl((int)(rdy >> 32), 0);
+    s.pw_out = 0;
+    if (s.pw_out_pos == want) break;
+    s.pw_discards++;  // (the walk left the grid: a sequential window, an iteration that outran its record)
+  }
+  const long long ta1 = cycle_now();
+  s.pw_cyc[0] += ta1 - ta0;
+  if (l == 0) m.helper[0] = HELPER_PIPE_COPY;
+  Warp::sync();
+  cta_bar(1);
+  cta_bar(2);
+  s.pw_cur = want;
+  pipe_request(m, s, want + PIPE_WIN);  // the builder goes on with the next window of the grid
+  s.pw_cyc[1] += cycle_now() - ta1;
+  return applied;
+}
+
+// The records in ws are right for the graph after `applied` accepted moves; repair them for the moves
+// accepted since: the ones the builder had not seen when it built the window, and the ones a
+// sequential window applied while the walk stayed inside the window.
+template <int KMAX>
+__device__ __forceinline__ void pipe_catch_up(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
+                                              WindowSlots& ws, int applied, int fresh) {
+  PipeLink* lk = m.pipe;
+  const int l = Warp::lane();
+  const int64_t want = s.pw_cur;
+  const int from = (int)(s.read_pos - want), now = s.n_moves;
+  const long long ta2 = cycle_now();
+  s.pw_seen = now;
+  if (now == applied && !(m.pipe_debug && fresh)) return;
+  RoundCtx rc;
+  rc.pos = want; rc.hi = rng.gen_hi;
+  rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+  rc.redo_from = from;
+  if (now - applied > PIPE_LOG || (m.pipe_debug && fresh)) {  // more moves than the chain remembers: every record is built again
+    rc.redo_mode = 2;
+    s.pw_rebuilds++;
+    team_records<KMAX, true>(p, m, rc, rng.ubuf, ws);
+    return;
+  }
+  int flags = 0;
+  for (int i = applied + l; i < now; i += Warp::NL) flags |= lk->log[i % PIPE_LOG];
+  const int any_anc = Warp::ballot(flags & LOG_ANC) != 0u, any_hp = Warp::ballot(flags & LOG_HP) != 0u;
+  if (l == 0) {
+    m.helper[8] = from; m.helper[5] = applied; m.helper[6] = now; m.helper[7] = any_anc;
+    m.helper[0] = HELPER_REPAIR_BATCH;
+  }
+  Warp::sync();
+  cta_bar(1);
+  cta_bar(2);
+  const long long ta3 = cycle_now();
+  s.pw_cyc[2] += ta3 - ta2;
+  if (any_hp) {  // deletion draws index into the set of nodes with parents: those records are redone
+    rc.redo_mode = 0;
+    team_records<KMAX, true>(p, m, rc, rng.ubuf, ws);
+    s.pw_cyc[3] += cycle_now() - ta3;
+  }
+}
+
+// One pass over (what is left of) a window: walk / commit / repair epochs as in run_round; the
+// records come from the builder, and a stale record under the walk is rebuilt in place.
+template <int KMAX>
+__device__ __forceinline__ void run_round_pipe(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
+                                               WindowSlots& ws) {
+  long long t0 = cycle_now();
+  {
+    const bool fresh = s.pw_cur < 0 || s.read_pos < s.pw_cur || s.read_pos >= s.pw_cur + PIPE_WIN;
+    const int applied = fresh ? pipe_acquire<KMAX>(p, m, s, rng, ws) : s.pw_seen;
+    pipe_catch_up<KMAX>(p, m, s, rng, ws, applied, fresh ? 1 : 0);
+  }
+  RoundCtx rc;
+  rc.pos = s.pw_cur; rc.hi = rng.gen_hi;
+  rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+  rc.redo_from = -1; rc.redo_mode = 0;
+  while (s.next_log < (int)s.iter) s.next_log += p.output_every;  // (after sequential windows; else no step)
+  s.cyc[1] += cycle_now() - t0;
+  int k = (int)(s.read_pos - s.pw_cur);
+  for (;;) {
+    t0 = cycle_now();
+    int want = WIN < Warp::NL ? WIN : Warp::NL;  // one lane per iteration of the epoch
+    if ((int64_t)want > p.n_iter - s.iter) want = (int)(p.n_iter - s.iter);
+    if (want <= 0) break;
+    int stop = 0, accepted = 0, c = 0, type = 0;
+    const int nh0 = s.n_haspar;
+    const int n = round_epoch<KMAX>(p, m, s, ws, rc.pos, &k, want, &stop, &accepted, &c, &type);
+    s.cyc[2] += cycle_now() - t0;
+    if (n > 0) { s.need_full = 0; s.slots_sim += n; }
+    if (stop) {
+      if (stop == WALK_STALE) {
+        // an accepted move changed what this record depends on: the stale records behind the walk
+        // are built again from the current graph, and the walk goes on
+        t0 = cycle_now();
+        rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+        rc.redo_from = k; rc.redo_mode = 1;
+        s.pw_rebuilds++;
+        team_records<KMAX, true>(p, m, rc, rng.ubuf, ws);
+        s.cyc[1] += cycle_now() - t0;
+        s.pw_cyc[4] += cycle_now() - t0;
+        continue;
+      }
+      // one iteration needs more uniforms than a record can count: the sequential path takes it
+      if (stop == WALK_OVF) s.need_full = 1;
+      break;  // WALK_END: the next window
+    }
+    if (n == 0) break;
+    if (accepted) {
+      if (s.te_true < 4) break;  // (sequential windows take over)
+      if (k >= PIPE_WIN) break;
+      const int unfull = (type == 2 && m.npar[c] == p.max_par - 1) ? 1 : 0;
+      t0 = cycle_now();
+      team_repair(p, m, ws, c, unfull, s.anc_changed, k);
+      if (s.n_haspar != nh0) {
+        rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+        rc.redo_from = k; rc.redo_mode = 0;
+        team_records<KMAX, true>(p, m, rc, rng.ubuf, ws);
+      }
+      s.pw_seen = s.n_moves;
+      s.cyc[2] += cycle_now() - t0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Two-CTA pipeline, builder side (rank 1, its chain warp; the helper warps sit in helper_loop).
+// ---------------------------------------------------------------------------
+template <int KMAX>
+__device__ __forceinline__ void shadow_loop(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
+                                            WindowSlots& ws) {
+  const int l = Warp::lane();
+  chain_init<KMAX>(p, m, s, rng);
+  const WhJump jump = wh_jump_for_thread();
+  PipeLink* lk = m.pipe;
+  int seq = 0;
+  for (;;) {
+    // the replica follows the chain: same move, same team operations on this CTA's copy
+    int w0, w1, w2, w3;
+    ld_poll128(&lk->mq[s.n_moves % PIPE_MQ][0], w0, w1, w2, w3);
+    if (w0 == s.n_moves + 1 && ((uint32_t)w1 >> 27) == (uint32_t)((s.n_moves + 1) & 31)) {
+      if (l == 0) st_peer(peer_addr(&lk->mq_tail, 0), s.n_moves + 1);  // (the message is in registers)
+      const double sc = __longlong_as_double(((long long)w3 << 32) | (long long)(uint32_t)w2);
+      apply_move_vals<KMAX>(p, m, s, 0, ((w1 >> 22) & 1) + 1, w1 & 0x7ff, (w1 >> 11) & 0x7ff, (w1 >> 23) & 7, sc,
+                            (w1 >> 26) & 1, nullptr);
+      continue;
+    }
+    if (ld_poll(&lk->req_exit)) break;
+    const unsigned long long req = ld_poll64(&lk->req);
+    if ((int)(req & 0xffffull) == seq) continue;
+    seq = (int)(req & 0xffffull);
+    const int64_t pos = (int64_t)(req >> 16);
+    if (rng.kind == RNG_WH) team_fill_wh(m, rng, pos, jump);
+    else rng_top_up(rng, pos);
+    RoundCtx rc;
+    rc.pos = pos; rc.hi = rng.gen_hi;
+    rc.n_haspar = s.n_haspar; rc.te_true = s.te_true; rc.agree_true = s.agree_true;
+    rc.redo_from = -1; rc.redo_mode = 0;
+    team_records<KMAX, true>(p, m, rc, rng.ubuf, ws);
+    // (the records are in this CTA's shared memory -- team_records ends with a CTA barrier -- before the flag leaves)
+    if (l == 0) st_peer64(peer_addr(&lk->rdy, 0), ((unsigned long long)(uint32_t)s.n_moves << 32) | (unsigned long long)seq);
+    Warp::sync();
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------
 // The whole chain.
 // ---------------------------------------------------------------------------
-template <int KMAX>
+// PIPE (device only): the two-CTA form -- the records of a window come from the builder CTA
+template <int KMAX, bool PIPE = false>
 BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStream& rng,
                      WindowSlots& ws) {
   const int l = Warp::lane();
   chain_init<KMAX>(p, m, s, rng);
-  for (int i = REPLAY_POS + l; i < 2 * REPLAY_POS; i += Warp::NL) ws.t_walk[i] = WALK_END;
+  for (int i = (PIPE ? PIPE_WIN : REPLAY_POS) + l; i < 2 * REPLAY_POS; i += Warp::NL) ws.t_walk[i] = WALK_END;
   Warp::sync();
 #if defined(__CUDA_ARCH__)
   const WhJump jump = wh_jump_for_thread();
@@ -1886,7 +2302,10 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
     s.windows++;
     // position-parallel rounds need `TotalEdges < 3` to be impossible
     if (s.te_true >= 4 && s.te_m >= 3 && !s.need_full) {
-      run_round<KMAX>(p, m, s, rng, ws);
+#if defined(__CUDA_ARCH__)
+      if constexpr (PIPE) { run_round_pipe<KMAX>(p, m, s, rng, ws); continue; }
+#endif
+      if constexpr (!PIPE) run_round<KMAX>(p, m, s, rng, ws);
       continue;
     }
     // sequential windows (first iterations of a chain, tiny graphs)

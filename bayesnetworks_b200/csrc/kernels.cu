@@ -1,6 +1,7 @@
 // K2 (batched proposal scoring), K3 (chains), K4 (node scores) -- device entry points.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -122,13 +123,176 @@ __global__ void __launch_bounds__((HELPER_WARPS + 1) * 32, 1) chain_kernel(Chain
     for (int t = 0; t < 12; t++) r.cyc[t] = s.cyc[t];
     r.slots_sim = s.slots_sim;
     r.cyc_total = clk1 - clk0;
+    for (int t = 0; t < 4; t++) r.pipe[t] = 0;
+    for (int t = 0; t < 6; t++) r.pipe_cyc[t] = 0;
   }
+}
+
+// ---------------------------------------------------------------------------
+// K3, two-CTA form (chain_core.cuh: "Two-CTA pipeline"): a chain is a cluster of two CTAs on two
+// SMs.  Rank 0 is the chain (walk, commit, accepted moves); rank 1 keeps a replica of the graph
+// state and builds the position records of the next window meanwhile.  Only launched when the whole
+// per-chain state fits in shared memory (each CTA holds its own copy) and MaxPar <= 8.
+// The two roles are separate __noinline__ functions: compiled into one body, the register allocation
+// of either role suffers from the other (measured: the ancestor updates of the chain ran at half
+// speed).  Everything the roles share sits in DYNAMIC shared memory at plan offsets, so that each
+// function derives its pointers from the shared-memory symbol itself (LDS/STS, and the same
+// address in both CTAs for mapa).
+// ---------------------------------------------------------------------------
+struct PipeRoleMem {
+  ChainMem m;
+  double* ubuf; WindowSlots* ws; double* dof_ratio; uint8_t* types;
+};
+
+template <int KMAX>
+__device__ __forceinline__ PipeRoleMem pipe_role_setup(const ChainParams& p, const ChainWorkspace& w, const ChainSmemPlan& sm,
+                                                      int rank, int ch, unsigned char* dyn_smem) {
+  PipeRoleMem r;
+  ChainMem& m = r.m;
+  const int64_t P = p.P, MP = p.max_par;
+  m.par = (int*)(dyn_smem + sm.off_par);
+  m.npar = (int*)(dyn_smem + sm.off_npar);
+  m.base = (double*)(dyn_smem + sm.off_base);
+  m.anc = (uint32_t*)(dyn_smem + sm.off_anc);
+  m.haspar = (uint32_t*)(dyn_smem + sm.off_haspar);
+  m.hp_list = (int*)(dyn_smem + sm.off_hplist);
+  m.scratch = (int*)(dyn_smem + sm.off_scratch);
+  m.nver = (uint32_t*)(dyn_smem + sm.off_nver);
+  const int64_t cap = p.trace_capacity;
+  m.t_iter = w.t_iter + ch * cap; m.t_changed = w.t_changed + ch * cap;
+  m.t_movetype = w.t_movetype + ch * cap; m.t_gll = w.t_gll + ch * cap;
+  m.t_add = w.t_add + ch * cap; m.t_del = w.t_del + ch * cap;
+  m.t_fn = w.t_fn + ch * cap; m.t_fp = w.t_fp + ch * cap;
+  // the replica keeps no books: no birth iterations, tabulations, move log
+  m.born = rank == 0 ? w.born + ch * P * MP : nullptr;
+  m.moves = (rank == 0 && w.moves) ? w.moves + (int64_t)ch * p.moves_capacity * 4 : nullptr;
+  m.edge_freq = (rank == 0 && w.edge_freq) ? w.edge_freq + ch * P * P : nullptr;
+  m.npar_freq = (rank == 0 && w.npar_freq) ? w.npar_freq + ch * P * (MP + 1) : nullptr;
+  m.npar_since = (rank == 0 && w.npar_since) ? w.npar_since + ch * P : nullptr;
+  m.dscore = w.dscore + ch * P * MP * 2;  // (score, tag) pairs, shared by the two CTAs
+  m.fac = nullptr; m.rowbuf = nullptr;
+  m.helper = (volatile int*)(dyn_smem + sm.off_helper);
+  m.pipe = (PipeLink*)(dyn_smem + sm.off_link);
+  m.pipe_rank = rank;
+  m.pipe_debug = w.pipeline == 3 ? 1 : 0;
+  r.ubuf = (double*)(dyn_smem + sm.off_ubuf);
+  r.ws = (WindowSlots*)(dyn_smem + sm.off_ws);
+  r.dof_ratio = (double*)(dyn_smem + sm.off_dof);
+  r.types = (uint8_t*)(dyn_smem + sm.off_types);
+  return r;
+}
+
+__device__ __forceinline__ RngStream pipe_role_rng(const ChainRngArgs& ra, int rank, int ch, int n_chains, double* ubuf) {
+  RngStream rng;  // each CTA generates the chain's stream for itself
+  if (ra.kind == RNG_WH)
+    rng_init_wh(rng, ra.seeds[3 * ch], ra.seeds[3 * ch + 1], ra.seeds[3 * ch + 2], ubuf);
+  else if (ra.kind == RNG_RMT)
+    rng_init_rmt(rng, ra.mt_states + ((int64_t)rank * n_chains + ch) * 624, ra.mt_pos[ch], ubuf);
+  else
+    rng_init_replay(rng, ra.replay + (int64_t)ch * ra.replay_len, ra.replay_len, ubuf);
+  return rng;
+}
+
+template <int KMAX>
+__device__ __forceinline__ void pipe_role_chain(ChainParams p, ChainWorkspace w, ChainRngArgs ra, ChainSmemPlan sm,
+                                             ChainResult* results) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x >> 1;
+  PipeRoleMem r = pipe_role_setup<KMAX>(p, w, sm, 0, ch, dyn_smem);
+  ChainMem& m = r.m;
+  RngStream rng = pipe_role_rng(ra, 0, ch, gridDim.x >> 1, r.ubuf);
+  set_row_geom(p);
+  p.sc.half_n = (double)p.n_samples / 2.0;
+  p.sc.ratio = r.dof_ratio;
+  if (!m.moves) p.moves_capacity = 0;
+  p.node_type = r.types;
+  if (warp != 0) {  // helper warps: parked on a named barrier until the chain needs them
+    helper_loop<KMAX, true>(p, m, warp, r.ubuf, *r.ws);
+    return;
+  }
+  ChainScalars s;
+  const long long clk0 = clock64();
+  run_chain<KMAX, true>(p, m, s, rng, *r.ws);
+  const long long clk1 = clock64();
+  if (lane == 0) { st_peer(peer_addr(&m.pipe->req_exit, 1), 1); m.helper[0] = HELPER_EXIT; }
+  __syncwarp();
+  cta_bar(1);
+  const int64_t P = p.P, MP = p.max_par;
+  int* g_par = w.par + ch * P * MP;
+  int* g_npar = w.npar + ch * P;
+  for (int64_t i = lane; i < P * MP; i += 32) g_par[i] = m.par[i];
+  for (int64_t i = lane; i < P; i += 32) g_npar[i] = m.npar[i];
+  if (lane == 0) {
+    ChainResult& o = results[ch];
+    o.uniforms = s.read_pos;
+    o.valid_iters = s.valid_iters;
+    o.alg_bytes = s.alg_bytes;
+    for (int t = 0; t < 3; t++) { o.proposed[t] = s.proposed[t]; o.reject[t] = s.reject[t]; }
+    o.n_nonpd = s.n_nonpd;
+    o.total_edges = s.te_true;
+    o.status = s.status;
+    o.windows = s.windows;
+    o.n_rows = s.n_rows;
+    o.n_moves = s.n_moves;
+    for (int t = 0; t < 12; t++) o.cyc[t] = s.cyc[t];
+    o.slots_sim = s.slots_sim;
+    o.cyc_total = clk1 - clk0;
+    for (int t = 0; t < 6; t++) o.pipe_cyc[t] = s.pw_cyc[t];
+    o.pipe[0] = s.pw_out_seq; o.pipe[1] = s.pw_waits; o.pipe[2] = s.pw_discards; o.pipe[3] = s.pw_rebuilds;
+  }
+}
+
+template <int KMAX>
+__device__ __forceinline__ void pipe_role_builder(ChainParams p, ChainWorkspace w, ChainRngArgs ra, ChainSmemPlan sm) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x >> 1;
+  PipeRoleMem r = pipe_role_setup<KMAX>(p, w, sm, 1, ch, dyn_smem);
+  ChainMem& m = r.m;
+  RngStream rng = pipe_role_rng(ra, 1, ch, gridDim.x >> 1, r.ubuf);
+  set_row_geom(p);
+  p.sc.half_n = (double)p.n_samples / 2.0;
+  p.sc.ratio = r.dof_ratio;
+  p.moves_capacity = 0;
+  p.node_type = r.types;
+  if (warp != 0) {
+    helper_loop<KMAX, true>(p, m, warp, r.ubuf, *r.ws);
+    return;
+  }
+  ChainScalars s;
+  shadow_loop<KMAX>(p, m, s, rng, *r.ws);
+  if (lane == 0) m.helper[0] = HELPER_EXIT;
+  __syncwarp();
+  cta_bar(1);
+}
+
+template <int KMAX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((HELPER_WARPS + 1) * 32, 1)
+    chain_pipe_kernel(ChainParams p, ChainWorkspace w, ChainRngArgs ra, ChainSmemPlan sm, ChainResult* __restrict__ results) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  {
+    // (N - 1) / (N - k - 1), src/network.h:232-234; node types; an empty mailbox
+    double* dof = (double*)(dyn_smem + sm.off_dof);
+    for (int k = threadIdx.x; k < KMAX + 2; k += blockDim.x) dof[k] = (double)(p.n_samples - 1) / (double)(p.n_samples - k - 1);
+    uint8_t* t = (uint8_t*)(dyn_smem + sm.off_types);
+    for (int i = threadIdx.x; i < p.P; i += blockDim.x) t[i] = p.node_type[i];
+    int* lk = (int*)(dyn_smem + sm.off_link);
+    for (int i = threadIdx.x; i < (int)(sizeof(PipeLink) / 4); i += blockDim.x) lk[i] = 0;
+  }
+  __syncthreads();
+  cluster_sync_all();  // both mailboxes are initialised before anybody writes into the peer's
+  if (rank == 0) pipe_role_chain<KMAX>(p, w, ra, sm, results);
+  else pipe_role_builder<KMAX>(p, w, ra, sm);
+  cluster_sync_all();  // nobody leaves while the peer may still touch its shared memory
 }
 
 // Greedy placement of the per-chain arrays into the CTA's dynamic shared memory, hottest
 // and smallest first; the ancestor bitsets get an odd row stride so that the column scan
 // of anc_after_add/delete (one row per lane) is bank-conflict free.
-static ChainSmemPlan plan_chain_smem(ChainParams& p, int scratch_n, int budget) {
+static ChainSmemPlan plan_chain_smem(ChainParams& p, int scratch_n, int budget, bool with_nver = false) {
   ChainSmemPlan sm;
   int used = 0;
   auto place = [&](int64_t bytes) -> int {
@@ -140,7 +304,16 @@ static ChainSmemPlan plan_chain_smem(ChainParams& p, int scratch_n, int budget) 
   };
   const int64_t P = p.P, MP = p.max_par, W = p.W;
   sm.off_types = place(P);
+  sm.off_ubuf = sm.off_ws = sm.off_helper = sm.off_dof = sm.off_link = -1;
+  if (with_nver) {  // two-CTA form: what the one-CTA kernel keeps in static shared memory
+    sm.off_ubuf = place(RNG_CAP * 8);
+    sm.off_ws = place(sizeof(WindowSlots));
+    sm.off_helper = place(HELPER_WORDS * 4);
+    sm.off_dof = place((8 + 2) * 8);
+    sm.off_link = place(sizeof(PipeLink));
+  }
   sm.off_npar = place(P * 4);
+  sm.off_nver = with_nver ? place(P * 4) : -1;
   sm.off_base = place(P * 8);
   sm.off_haspar = place(W * 4);
   sm.off_hplist = place(P * 4);
@@ -156,9 +329,44 @@ static ChainSmemPlan plan_chain_smem(ChainParams& p, int scratch_n, int budget) 
   return sm;
 }
 
+// the two-CTA form, when the whole state (plus the move counts) fits next to its static shared memory
+template <int KMAX>
+static bool plan_pipe(ChainParams& p, int scratch_n, ChainSmemPlan* out) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, chain_pipe_kernel<KMAX>) != cudaSuccess) { cudaGetLastError(); return false; }
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int budget = max_optin - (int)fa.sharedSizeBytes - 1024;
+  ChainParams q = p;
+  const ChainSmemPlan sm = plan_chain_smem(q, scratch_n, budget > 0 ? budget : 0, true);
+  const bool all = sm.off_link >= 0 && sm.off_types >= 0 && sm.off_npar >= 0 && sm.off_nver >= 0 && sm.off_base >= 0 && sm.off_haspar >= 0 &&
+                   sm.off_hplist >= 0 && sm.off_par >= 0 && sm.off_scratch >= 0 && sm.off_anc >= 0;
+  if (!all || p.P > PIPE_MAX_NODES) return false;
+  p = q;
+  *out = sm;
+  return true;
+}
+
+bool chains_can_pipeline(ChainParams p, int scratch_n) {
+  if (p.max_par > 8) return false;
+  ChainSmemPlan sm;
+  return plan_pipe<8>(p, scratch_n, &sm);
+}
+
 template <int KMAX>
 static const char* launch_chains_t(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
                                    ChainResult* d_results, int n_chains, cudaStream_t stream) {
+  if constexpr (KMAX <= 8) {
+    ChainSmemPlan psm;
+    if (w.pipeline && plan_pipe<KMAX>(p, w.scratch_n, &psm)) {
+      if (cudaFuncSetAttribute(chain_pipe_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, psm.total_bytes) != cudaSuccess)
+        return "cudaFuncSetAttribute(chain_pipe_kernel) failed";
+      chain_pipe_kernel<KMAX><<<2 * n_chains, (HELPER_WARPS + 1) * 32, psm.total_bytes, stream>>>(p, w, ra, psm, d_results);
+      return nullptr;
+    }
+    if (w.pipeline) return "two-CTA chains requested but the state does not fit in shared memory";
+  }
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, chain_kernel<KMAX, true>) != cudaSuccess) return "cudaFuncGetAttributes failed";
   int dev = 0, max_optin = 0;
@@ -171,6 +379,18 @@ static const char* launch_chains_t(ChainParams p, const ChainWorkspace& w, const
   auto kernel = all_smem ? chain_kernel<KMAX, true> : chain_kernel<KMAX, false>;
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm.total_bytes) != cudaSuccess)
     return "cudaFuncSetAttribute(chain_kernel) failed";
+  if (getenv("BN_B200_CLUSTER_EXPERIMENT") && n_chains % 2 == 0) {
+    // (experiment) the one-CTA kernel launched as clusters of two independent chains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_chains); cfg.blockDim = dim3((HELPER_WARPS + 1) * 32);
+    cfg.dynamicSmemBytes = sm.total_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, p, w, ra, sm, d_results) != cudaSuccess) return "cluster launch failed";
+    return nullptr;
+  }
   kernel<<<n_chains, (HELPER_WARPS + 1) * 32, sm.total_bytes, stream>>>(p, w, ra, sm, d_results);
   return nullptr;
 }

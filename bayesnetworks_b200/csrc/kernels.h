@@ -18,13 +18,16 @@ struct ChainWorkspace {  // arrays over all chains of a run (device memory)
   double* dscore;                      // [nc][P][max_par] deletion-score cache (all-ones = unknown)
   double* fac;                         // [nc][P][fac_stride(max_par)] per-node Cholesky factors
   double* rowbuf;                      // [nc][REPLAY_POS][row_stride(max_par)] candidate rows of a round
+  int pipeline;                        // 1: two CTAs per chain (chain_pipe_kernel): dscore holds (score, tag) pairs,
+                                       // the R-MT states are [2][nc][624] (one copy per CTA)
 };
 
 // Which per-chain arrays live in dynamic shared memory (byte offset, -1 = global memory).
 // One chain = one CTA, so the hot state (parent lists, scores, ancestor bitsets) sits
 // ~30 cycles away instead of an L2 round trip; arrays that do not fit stay in global.
 struct ChainSmemPlan {
-  int off_types, off_npar, off_base, off_haspar, off_hplist, off_par, off_scratch, off_anc;
+  int off_types, off_npar, off_base, off_haspar, off_hplist, off_par, off_scratch, off_anc, off_nver;
+  int off_ubuf, off_ws, off_helper, off_dof, off_link;  // two-CTA form only
   int total_bytes;
 };
 
@@ -45,6 +48,8 @@ struct ChainResult {
   int proposed[3], reject[3];
   int n_nonpd, total_edges, status, windows, n_rows, n_moves;
   long long cyc[12], slots_sim, cyc_total;
+  long long pipe_cyc[6];
+  int pipe[4];  // two-CTA form: windows requested, waits for the builder, windows discarded, in-place rebuilds
 };
 
 struct SweepParams {
@@ -57,6 +62,8 @@ struct SweepParams {
   double* out_base; double* out_score; double* out_log_hr;
 };
 
+// true when launch_chains can run the two-CTA form for this shape (MaxPar <= 8, state fits in shared memory)
+bool chains_can_pipeline(ChainParams p, int scratch_n);
 const char* launch_chains(ChainParams p, const ChainWorkspace& w, const ChainRngArgs& ra,
                           ChainResult* d_results, int n_chains, cudaStream_t stream);
 const char* launch_score_nodes(const double* C, int64_t ldc, int n_samples, int max_par, int n_items,
