@@ -896,6 +896,8 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
       s.slots_simulated = res[ch].slots_sim;
       s.kernel_cycles = res[ch].cyc_total;
     }
+    if ((res[ch].status == 91 || res[ch].status == 92) && !rc)
+      rc = fail(BN_ERR_CUDA, "chain %d: the two CTAs of the chain lost each other (mailbox watchdog %d)", ch, res[ch].status);
     if (res[ch].status == BN_ERR_NO_LEGAL_PROPOSAL && !rc)
       rc = fail(res[ch].status, "chain %d: no legal proposal exists (every candidate child is a source or full, or every candidate parent a sink / already a parent)", ch);
     if (a->rng_kind == BN_RNG_REPLAY && (res[ch].uniforms > a->replay_len || res[ch].status == BN_ERR_CAPACITY) && !rc)

@@ -469,12 +469,12 @@ __device__ __forceinline__ void st_peer128(uint32_t a, int x, int y, int z, int 
 // polls of this CTA's own mailbox (the peer writes it remotely)
 __device__ __forceinline__ int ld_poll(const int* p) {
   int v;
-  asm volatile("ld.relaxed.cluster.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long ld_poll64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.relaxed.cluster.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(smem_addr(p)) : "memory");
+  asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(v) : "r"(smem_addr(p)) : "memory");
   return v;
 }
 __device__ __forceinline__ void ld_poll128(const int* p, int& x, int& y, int& z, int& w) {
@@ -498,7 +498,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void pipe_publish(const ChainMem& m, int n, int type, int c, int j, int del, int ag,
                                              double score, int flags) {
   PipeLink* lk = m.pipe;
-  while (n - ld_poll(&lk->mq_tail) >= PIPE_MQ) {}
+  for (long long spins = 0; n - ld_poll(&lk->mq_tail) >= PIPE_MQ; spins++)
+    if (spins > (1ll << 27)) { lk->pad1 = 92; break; }  // (watchdog: the builder is gone -- run_chain reports it)
   const long long sb = __double_as_longlong(score);
   st_peer128(peer_addr(&lk->mq[n % PIPE_MQ][0], 1), n + 1,
              c | (j << 11) | ((type - 1) << 22) | (del << 23) | (ag << 26) | ((n + 1) << 27),
@@ -2106,9 +2107,10 @@ __device__ __forceinline__ int pipe_acquire(const ChainParams& p, ChainMem& m, C
     if (!s.pw_out) pipe_request(m, s, want);
     unsigned long long rdy = 0ull;
     if (l == 0) {
-      int spins = 0;
-      while ((int)((rdy = ld_poll64(&lk->rdy)) & 0xffffull) != (s.pw_out_seq & 0xffff)) spins = 1;
-      s.pw_waits += spins;
+      long long spins = 0;
+      while ((int)((rdy = ld_poll64(&lk->rdy)) & 0xffffull) != (s.pw_out_seq & 0xffff))
+        if (++spins > (1ll << 27)) { lk->pad1 = 91; break; }  // (watchdog)
+      s.pw_waits += spins ? 1 : 0;
     }
     applied = Warp::shfl((int)(rdy >> 32), 0);
     s.pw_out = 0;
@@ -2290,6 +2292,10 @@ BN_HD void run_chain(const ChainParams& p, ChainMem& m, ChainScalars& s, RngStre
   while (s.iter < p.n_iter && s.status == 0) {
     long long t0 = cycle_now();
 #if defined(__CUDA_ARCH__)
+    if constexpr (PIPE) {
+      const int wd = m.pipe->pad1;  // a mailbox watchdog fired (the peer CTA stopped answering): an error, never a hang
+      if (wd) { s.status = wd; break; }
+    }
     if (rng.kind == RNG_WH && m.helper) {
       // the CTA appends 128 uniforms at a time (>= 385 ahead of the read position afterwards)
       team_fill_wh(m, rng, s.read_pos, jump);
