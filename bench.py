@@ -457,6 +457,25 @@ def run_ours(a):
         except Exception as exc:
             roofline["two_cta_form"] = f"failed: {type(exc).__name__}: {exc}"
 
+    if world == 1 and not a.no_configs:
+        # every SM busy: the workload's 64 chains light 64 of the 148 SMs (one CTA per chain, the chain is a
+        # latency-bound dependent instruction stream); the same run with one chain per SM shows what the GPU
+        # sustains on this path.  Reported beside the headline, which stays at BASELINE's 64 chains.
+        try:
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            with Context.from_device(X.data_ptr(), a.samples, a.samples, a.nodes, g.source, g.target, nt,
+                                     max_par=a.max_par, device=local_rank) as ctx:
+                res3, ms3 = ctx.run(n_chains=n_sm, n_iter=a.iters, output=a.output, rng="wh", seeds=chain_seeds(n_sm))
+            roofline["one_chain_per_sm"] = {
+                "chains": n_sm, "chain_kernel_ms": ms3,
+                "proposals_per_sec": sum(r.valid_iters for r in res3) / (ms3 * 1e-3),
+                "iters_per_sec": n_sm * a.iters / (ms3 * 1e-3),
+                "sm_cycles_per_iteration_per_chain": max(r.kernel_cycles for r in res3) / a.iters,
+                "first_64_chains_same_as_headline_run": bool(all(
+                    np.array_equal(r.trace["ChangedNode"], c) for r, c in zip(res3[:n_chains_total], state["res"]["changed"])))}
+        except Exception as exc:
+            roofline["one_chain_per_sm"] = f"failed: {type(exc).__name__}: {exc}"
+
     if not a.no_kernels and world == 1:   # (the sweep is timed on the chains' final graphs)
         line["kernels"] = side_kernels(a, X, g, nt, r0.get("results"), local_rank, hbm_peak)
     if not a.no_configs:
