@@ -569,17 +569,25 @@ static int sweep_device(bn_ctx* c, int n_graphs, const int* d_parents, const int
   CU_TRY(pool_alloc((void**)&d_te, (size_t)n_graphs * 4));
   cudaError_t e = pool_alloc((void**)&d_ag, (size_t)n_graphs * 4);
   if (e != cudaSuccess) { pool_free(d_te); return fail(BN_ERR_OOM, "sweep scratch"); }
+  int* d_order = nullptr;
+  {
+    const char* so = getenv("BN_B200_SWEEP_ORDER");  // (A/B switch: 0 = natural order)
+    if (!(so && so[0] == '0') && (int64_t)n_graphs * c->P < (1ll << 31)) {
+      e = pool_alloc((void**)&d_order, (size_t)n_graphs * c->P * 4);
+      if (e != cudaSuccess) { pool_free(d_te); pool_free(d_ag); return fail(BN_ERR_OOM, "sweep scratch"); }
+    }
+  }
   SweepParams sp;
   sp.P = c->P; sp.max_par = c->max_par; sp.n_graphs = n_graphs; sp.n_samples = c->n_samples;
   sp.n_sim_edges = c->n_sim_edges; sp.C = c->d_C; sp.ldc = c->P; sp.diag = c->d_diag;
   sp.node_type = c->d_node_type; sp.sim_edge = c->d_sim_edge; sp.phi = c->phi; sp.omega = c->omega;
-  sp.parents = d_parents; sp.n_par = d_npar; sp.te = d_te; sp.agree = d_ag;
+  sp.parents = d_parents; sp.n_par = d_npar; sp.te = d_te; sp.agree = d_ag; sp.order = d_order;
   sp.out_base = d_base; sp.out_score = d_score; sp.out_log_hr = d_hr;
   cudaEvent_t ev0, ev1;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   cudaEventRecord(ev0, c->stream);
   const char* msg = launch_sweep(sp, c->stream);
-  c->launches += 2;
+  c->launches += d_order ? 3 : 2;
   cudaEventRecord(ev1, c->stream);
   int rc = BN_OK;
   if (msg) rc = fail(BN_ERR_UNSUPPORTED, "%s", msg);
@@ -589,6 +597,7 @@ static int sweep_device(bn_ctx* c, int n_graphs, const int* d_parents, const int
   if (!rc && kernel_ms) cudaEventElapsedTime(kernel_ms, ev0, ev1);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   pool_free(d_te); pool_free(d_ag);
+  if (d_order) pool_free(d_order);
   return rc;
 }
 

@@ -59,6 +59,7 @@ struct SweepParams {
   double phi, omega;
   const int* parents; const int* n_par;   // [g][P][max_par], [g][P]
   int* te; int* agree;                     // [g] scratch
+  int* order;                              // [g*P] scratch: items by falling parent count (null: natural order)
   double* out_base; double* out_score; double* out_log_hr;
 };
 
