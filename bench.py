@@ -432,32 +432,6 @@ def run_ours(a):
         line["strong_64_chains"] = strong
 
     if world == 1 and not a.no_configs:
-        # the opt-in two-CTA form of the chain kernel (BN_B200_PIPE=1, profiles/r02_two_cta_chain.md) on the
-        # same workload: a reported comparison, outside every timed region of the headline
-        try:
-            old_env = os.environ.get("BN_B200_PIPE")
-            os.environ["BN_B200_PIPE"] = "1"
-            try:
-                with Context.from_device(X.data_ptr(), a.samples, a.samples, a.nodes, g.source, g.target, nt,
-                                         max_par=a.max_par, device=local_rank) as ctx:
-                    ctx.run(n_chains=n_chains_total, n_iter=2000, output=a.output, rng="wh", seeds=chain_seeds(n_chains_total))
-                    res2, ms2 = ctx.run(n_chains=n_chains_total, n_iter=a.iters, output=a.output, rng="wh",
-                                        seeds=chain_seeds(n_chains_total))
-            finally:
-                if old_env is None:
-                    os.environ.pop("BN_B200_PIPE", None)
-                else:
-                    os.environ["BN_B200_PIPE"] = old_env
-            roofline["two_cta_form"] = {
-                "chain_kernel_ms": ms2, "sm_cycles_per_iteration_per_chain": max(r.kernel_cycles for r in res2) / a.iters,
-                "same_trajectories_as_one_cta": bool(all(
-                    np.array_equal(r.trace["ChangedNode"], c) for r, c in zip(res2, state["res"]["changed"]))),
-                "note": "a cluster of two CTAs per chain (128 SMs busy): rank 1 builds the next window's records "
-                        "while rank 0 walks; opt-in because it is not faster here (instruction-fetch bound)"}
-        except Exception as exc:
-            roofline["two_cta_form"] = f"failed: {type(exc).__name__}: {exc}"
-
-    if world == 1 and not a.no_configs:
         # every SM busy: the workload's 64 chains light 64 of the 148 SMs (one CTA per chain, the chain is a
         # latency-bound dependent instruction stream); the same run with one chain per SM shows what the GPU
         # sustains on this path.  Reported beside the headline, which stays at BASELINE's 64 chains.
@@ -607,21 +581,6 @@ def baseline_configs(local_rank):
                                  "largest_parent_set": int(r.final_npar.max()),
                                  "sm_cycles_per_iteration": r.kernel_cycles / 1e6}
     c3["maxpar50_over_maxpar8"] = c3["maxpar50"]["chain_kernel_ms"] / c3["maxpar8"]["chain_kernel_ms"]
-    # the same chain on the opt-in two-CTA form (records built on a second SM)
-    old_env = os.environ.get("BN_B200_PIPE")
-    os.environ["BN_B200_PIPE"] = "1"
-    try:
-        g3 = make_prior(dag, max_par=8, seed=43)
-        with Context.from_data(X3, g3.source, g3.target, g3.node_type_codes(), max_par=8, device=local_rank) as ctx:
-            ctx.run(n_chains=1, n_iter=1000, output=100)
-            res, ms = ctx.run(n_chains=1, n_iter=1000000, output=100, rng="wh")
-            c3["maxpar8_two_cta_form"] = {"chain_kernel_ms": ms, "iters_per_sec": 1e6 / (ms * 1e-3),
-                                          "sm_cycles_per_iteration": res[0].kernel_cycles / 1e6}
-    finally:
-        if old_env is None:
-            os.environ.pop("BN_B200_PIPE", None)
-        else:
-            os.environ["BN_B200_PIPE"] = old_env
     out["config3"] = c3
     return out
 
