@@ -746,7 +746,7 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
     const int sn = scratch_words((int)P, HELPER_WARPS, 32) > w.scratch_n ? scratch_words((int)P, HELPER_WARPS, 32) : w.scratch_n;
     w.pipeline = (e && e[0] != '0' && MP <= 8 && 2 * nc <= n_sm && chains_can_pipeline(q, sn)) ? 1 : 0;
     if (w.pipeline) w.scratch_n = sn;
-    if (w.pipeline && e && e[0] == '3') w.pipeline = 3;  // (developer switch: the chain's CTA rebuilds every window itself)
+    if (w.pipeline && e && (e[0] == '3' || e[0] == '5')) w.pipeline = e[0] - '0';  // (developer switch: the chain's CTA rebuilds every window itself)
   }
   const size_t dscore_n = (size_t)(nc * P * MP) * (w.pipeline ? 2 : 1);
   CU_TRY(buf.alloc(&w.par, (size_t)(nc * P * MP)));
@@ -905,6 +905,8 @@ extern "C" int bn_run(bn_ctx* c, const bn_run_args* a, bn_trace* trace, int* fin
       s.slots_simulated = res[ch].slots_sim;
       s.kernel_cycles = res[ch].cyc_total;
     }
+    if (res[ch].status == 95 && !rc)
+      rc = fail(BN_ERR_CUDA, "chain %d: an accepted move did not fit the graph (two-CTA form: a record escaped its repair)", ch);
     if ((res[ch].status == 91 || res[ch].status == 92) && !rc)
       rc = fail(BN_ERR_CUDA, "chain %d: the two CTAs of the chain lost each other (mailbox watchdog %d)", ch, res[ch].status);
     if (res[ch].status == BN_ERR_NO_LEGAL_PROPOSAL && !rc)

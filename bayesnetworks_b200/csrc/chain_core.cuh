@@ -1731,6 +1731,17 @@ template <int KMAX>
 BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, int64_t it, int type, int c,
                            int j, int del, double new_score, int ag, const double* newrow) {
   const int MP = p.max_par, l = Warp::lane();
+#if defined(__CUDA_ARCH__)
+  // Consistency guard (two-CTA form): a move that cannot be applied to the graph it arrives at -- an addition at a
+  // full node or of a parent already there, a deletion slot that does not hold the parent -- means a record
+  // escaped its repair.  The chain stops with status 95 instead of corrupting its state.
+  if (m.pipe) {
+    const int kk0 = m.npar[c];
+    bool bad = (type == 1) ? (kk0 >= MP) : (del < 0 || del >= kk0 || m.par[(int64_t)c * MP + del] != j);
+    if (type == 1) for (int e = 0; e < kk0 && e < MP; e++) bad |= m.par[(int64_t)c * MP + e] == j;
+    if (bad) { s.status = 95; return; }
+  }
+#endif
   int* pc = m.par + (int64_t)c * MP;
   int* bc = m.born ? m.born + (int64_t)c * MP : nullptr;  // (only read with edge_freq)
   const int k = m.npar[c];
@@ -1751,7 +1762,7 @@ BN_HD void apply_move_vals(const ChainParams& p, ChainMem& m, ChainScalars& s, i
   const int64_t first_counted = (it > p.drop) ? it : p.drop;  // Tabulate(): main.cpp:392
 #if defined(__CUDA_ARCH__)
   // two-CTA pipeline: the builder's replica starts on the move while this CTA applies it
-  const bool publish = m.pipe && m.pipe_rank == 0;
+  const bool publish = m.pipe && m.pipe_rank == 0 && m.pipe_debug != 2;  // (developer switch BN_B200_PIPE=5: no moves published)
   const long long tp0 = cycle_now();
   if (publish && l == 0)
     pipe_publish(m, s.n_moves, type, c, j, type == 2 ? del : 0, ag, new_score,

@@ -174,7 +174,7 @@ __device__ __forceinline__ PipeRoleMem pipe_role_setup(const ChainParams& p, con
   m.helper = (volatile int*)(dyn_smem + sm.off_helper);
   m.pipe = (PipeLink*)(dyn_smem + sm.off_link);
   m.pipe_rank = rank;
-  m.pipe_debug = w.pipeline == 3 ? 1 : 0;
+  m.pipe_debug = w.pipeline == 3 ? 1 : (w.pipeline == 5 ? 2 : 0);
   r.ubuf = (double*)(dyn_smem + sm.off_ubuf);
   r.ws = (WindowSlots*)(dyn_smem + sm.off_ws);
   r.dof_ratio = (double*)(dyn_smem + sm.off_dof);
