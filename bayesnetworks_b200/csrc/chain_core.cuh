@@ -26,6 +26,10 @@
 // Acyclicity (pathExists, src/network.h:366-413, a BFS per proposal) is an O(1) bit test against
 // per-node ancestor bitsets, maintained on accepted moves.
 //
+// An experimental second form (chain_pipe_kernel, opt-in) spreads a chain over a cluster of two CTAs: one walks,
+// commits and applies, the other keeps a replica of the graph and builds the records of the next window
+// ("Two-CTA pipeline" below; bit-identical, not faster, known rare hang: profiles/r02_two_cta_chain.md).
+//
 // The same source compiles for the host with a one-lane warp (tests/emu): the sequential logic is
 // checked against the oracle without a GPU.
 #pragma once
