@@ -28,7 +28,7 @@
 //
 // An experimental second form (chain_pipe_kernel, opt-in) spreads a chain over a cluster of two CTAs: one walks,
 // commits and applies, the other keeps a replica of the graph and builds the records of the next window
-// ("Two-CTA pipeline" below; bit-identical, not faster, known rare hang: profiles/r02_two_cta_chain.md).
+// ("Two-CTA pipeline" below; bit-identical, not faster: profiles/r02_two_cta_chain.md).
 //
 // The same source compiles for the host with a one-lane warp (tests/emu): the sequential logic is
 // checked against the oracle without a GPU.
@@ -2262,17 +2262,30 @@ __device__ __forceinline__ void shadow_loop(const ChainParams& p, ChainMem& m, C
   int seq = 0;
   for (;;) {
     // the replica follows the chain: same move, same team operations on this CTA's copy
-    int w0, w1, w2, w3;
-    ld_poll128(&lk->mq[s.n_moves % PIPE_MQ][0], w0, w1, w2, w3);
-    if (w0 == s.n_moves + 1 && ((uint32_t)w1 >> 27) == (uint32_t)((s.n_moves + 1) & 31)) {
+    // ONE lane reads the mailbox and the warp takes its values: 32 lanes polling for themselves are not
+    // guaranteed to execute a load together, and a message that lands between two lanes' loads splits the
+    // warp for good (some lanes serve the request, the others still wait for it with their own `seq` --
+    // the cause of a hang seen in about one launch in fifty before this was fixed)
+    int w0 = 0, w1 = 0, w2 = 0, w3 = 0, ex = 0, rq_lo = 0, rq_hi = 0;
+    if (l == 0) {
+      ld_poll128(&lk->mq[s.n_moves % PIPE_MQ][0], w0, w1, w2, w3);
+      ex = ld_poll(&lk->req_exit);
+      const unsigned long long rq = ld_poll64(&lk->req);
+      rq_lo = (int)(rq & 0xffffffffull); rq_hi = (int)(rq >> 32);
+    }
+    w0 = Warp::shfl(w0, 0);
+    const bool has_move = w0 == s.n_moves + 1;
+    if (has_move) { w1 = Warp::shfl(w1, 0); w2 = Warp::shfl(w2, 0); w3 = Warp::shfl(w3, 0); }  // (warp-uniform branch)
+    else { ex = Warp::shfl(ex, 0); rq_lo = Warp::shfl(rq_lo, 0); rq_hi = Warp::shfl(rq_hi, 0); }
+    if (has_move && ((uint32_t)w1 >> 27) == (uint32_t)((s.n_moves + 1) & 31)) {
       if (l == 0) st_peer(peer_addr(&lk->mq_tail, 0), s.n_moves + 1);  // (the message is in registers)
       const double sc = __longlong_as_double(((long long)w3 << 32) | (long long)(uint32_t)w2);
       apply_move_vals<KMAX>(p, m, s, 0, ((w1 >> 22) & 1) + 1, w1 & 0x7ff, (w1 >> 11) & 0x7ff, (w1 >> 23) & 7, sc,
                             (w1 >> 26) & 1, nullptr);
       continue;
     }
-    if (ld_poll(&lk->req_exit)) break;
-    const unsigned long long req = ld_poll64(&lk->req);
+    if (ex) break;
+    const unsigned long long req = ((unsigned long long)(uint32_t)rq_hi << 32) | (unsigned long long)(uint32_t)rq_lo;
     if ((int)(req & 0xffffull) == seq) continue;
     seq = (int)(req & 0xffffull);
     const int64_t pos = (int64_t)(req >> 16);

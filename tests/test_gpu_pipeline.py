@@ -4,10 +4,10 @@ the one-CTA kernel on the same inputs: every output bit for bit -- the two diffe
 and when, never in what a record says.  (The whole GPU suite also passes with BN_B200_PIPE=1 exported:
 profiles/r02_two_cta_chain.md.)
 
-Each case runs in a child process (tests/tools/pipe_case.py) with a time limit: the two-CTA kernel has a
-known, rare hang that is not located yet (about one launch in fifty at the benchmark's size, none seen at
-these sizes); a child that exceeds the limit is killed and the case reported as an expected failure with that
-reason instead of stalling the run.  A DIFFERENCE between the two forms is always a hard failure."""
+Each case runs in a child process (tests/tools/pipe_case.py) with a time limit: early builds of the two-CTA kernel
+had a rare hang (found and fixed: profiles/r02_two_cta_chain.md); should an experimental kernel ever stall again, the
+child is killed and the case reported as an expected failure instead of stalling the run.  A DIFFERENCE between the two
+forms is always a hard failure."""
 import json
 import os
 import subprocess
@@ -24,7 +24,7 @@ def _case(**spec):
     try:
         res = subprocess.run([sys.executable, TOOL, json.dumps(spec)], capture_output=True, text=True, timeout=150)
     except subprocess.TimeoutExpired:
-        pytest.xfail("the opt-in two-CTA kernel did not finish in 150 s (known rare hang, profiles/r02_two_cta_chain.md)")
+        pytest.xfail("the opt-in two-CTA kernel did not finish in 150 s (profiles/r02_two_cta_chain.md)")
     last = res.stdout.strip().splitlines()[-1] if res.stdout.strip() else ""
     assert res.returncode == 0 and last == "OK", (last, res.stderr[-2000:])
 

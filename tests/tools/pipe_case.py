@@ -1,6 +1,6 @@
 """Child process of tests/test_gpu_pipeline.py: one case on both forms of the chain kernel, compared bit for bit.
-Runs in its own process so that the (opt-in, experimental) two-CTA kernel can be given a time limit: a known,
-rare, not yet located hang of that kernel (profiles/r02_two_cta_chain.md) must not take the test run with it.
+Runs in its own process so that the (opt-in, experimental) two-CTA kernel can be given a time limit: a stall of
+that kernel (early builds had a rare one, profiles/r02_two_cta_chain.md) must not take the test run with it.
 usage: python pipe_case.py '<json spec>'  ->  prints OK or DIFF: <what>"""
 import json
 import os
