@@ -450,6 +450,27 @@ def run_ours(a):
         except Exception as exc:
             roofline["one_chain_per_sm"] = f"failed: {type(exc).__name__}: {exc}"
 
+    if world == 1 and not a.no_configs:
+        # the opt-in two-CTA form of the chain kernel (BN_B200_PIPE=1, profiles/r02_two_cta_chain.md) on the same
+        # workload, measured in a CHILD process with a time limit (an experimental kernel must not be able to
+        # take the headline run with it) and outside every timed region: a reported comparison
+        try:
+            env = dict(os.environ, BN_B200_PIPE="1", H2D="0", REPS="3", P=str(a.nodes), N=str(a.samples), MP=str(a.max_par),
+                       CHAINS=str(n_chains_total), ITERS=str(a.iters), CUDA_VISIBLE_DEVICES=str(local_rank))
+            res2 = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "gpu_perf.py")], capture_output=True,
+                                  text=True, timeout=150, env=env)
+            import re
+            m_ms = re.search(r"kernel ([0-9.]+) ms", res2.stdout)
+            m_cy = re.search(r"kernel cycles/iter/chain ([0-9.]+) \(max chain ([0-9.]+)\)", res2.stdout)
+            roofline["two_cta_form"] = {
+                "chain_kernel_ms": float(m_ms.group(1)), "sm_cycles_per_iteration_per_chain": float(m_cy.group(2)),
+                "one_cta_chain_kernel_ms": chain_ms,
+                "note": "a cluster of two CTAs per chain (128 SMs busy): rank 1 builds the next window's records while "
+                        "rank 0 walks; bit-identical (tests/test_gpu_pipeline.py), opt-in because it is not faster "
+                        "(instruction-fetch bound, profiles/r02_two_cta_chain.md)"}
+        except Exception as exc:
+            roofline["two_cta_form"] = f"not measured: {type(exc).__name__}: {exc}"
+
     if not a.no_kernels and world == 1:   # (the sweep is timed on the chains' final graphs)
         line["kernels"] = side_kernels(a, X, g, nt, r0.get("results"), local_rank, hbm_peak)
     if not a.no_configs:
