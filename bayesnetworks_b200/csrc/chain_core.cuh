@@ -2282,6 +2282,7 @@ __device__ __forceinline__ void shadow_loop(const ChainParams& p, ChainMem& m, C
       const double sc = __longlong_as_double(((long long)w3 << 32) | (long long)(uint32_t)w2);
       apply_move_vals<KMAX>(p, m, s, 0, ((w1 >> 22) & 1) + 1, w1 & 0x7ff, (w1 >> 11) & 0x7ff, (w1 >> 23) & 7, sc,
                             (w1 >> 26) & 1, nullptr);
+      if (s.status) break;  // (the move did not fit the replica: stop serving -- the chain's watchdog reports it)
       continue;
     }
     if (ex) break;
