@@ -400,7 +400,24 @@ const char* gram_build(const double* dX, int64_t ldx, int n_samples, int P, doub
 namespace {
 constexpr size_t STAGE_CHUNK = (size_t)8 << 20;
 constexpr int STAGE_BUFS = 4;
-constexpr int STAGE_THREADS = 4;
+constexpr int STAGE_THREADS_MAX = 16;
+// host threads that fill the pinned ring: 8 by default (the copy of 800 MB is bound by the host's memcpy rate
+// with 4: 62.8 ms per end-to-end step with 4 threads, 55.4 with 8, 52.3 from pinned memory); BN_B200_STAGE_THREADS overrides
+static int stage_threads() {
+  static int n = 0;
+  if (n == 0) {
+    const char* e = getenv("BN_B200_STAGE_THREADS");
+    if (e) {
+      n = atoi(e);
+    } else {
+      const int hw = (int)std::thread::hardware_concurrency();  // (half of the cores, at most 8)
+      n = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 2);
+    }
+    if (n < 1) n = 1;
+    if (n > STAGE_THREADS_MAX) n = STAGE_THREADS_MAX;
+  }
+  return n;
+}
 
 class StagePool {
  public:
@@ -415,7 +432,7 @@ class StagePool {
              cudaEventCreateWithFlags(&free_[b], cudaEventDisableTiming) == cudaSuccess;
       }
       if (ok) {
-        for (int t = 0; t < STAGE_THREADS; t++) workers_.emplace_back([this, t] { work(t); });
+        for (int t = 0; t < stage_threads(); t++) workers_.emplace_back([this, t] { work(t); });
         state_ = 1;
       } else {
         cudaGetLastError();
@@ -428,7 +445,7 @@ class StagePool {
   // dst[0..bytes) = src[0..bytes) by all workers; returns when done
   void copy(void* dst, const void* src, size_t bytes) {
     std::unique_lock<std::mutex> lk(mu_);
-    dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; pending_ = STAGE_THREADS; gen_++;
+    dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; pending_ = stage_threads(); gen_++;
     cv_.notify_all();
     done_.wait(lk, [this] { return pending_ == 0; });
   }
@@ -450,7 +467,7 @@ class StagePool {
       cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
       if (quit_) return;
       seen = gen_;
-      const size_t per = (bytes_ / STAGE_THREADS + 63) & ~(size_t)63;
+      const size_t per = (bytes_ / stage_threads() + 63) & ~(size_t)63;
       const size_t lo = per * t < bytes_ ? per * t : bytes_;
       const size_t hi = lo + per < bytes_ ? lo + per : bytes_;
       char* d = dst_; const char* s = src_;
